@@ -1,0 +1,183 @@
+"""Pin the CPU oracle against every known answer / assertion the reference's tests hold for
+the hot path.  No GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import dmrg, linalg, models, mps, tebd, tensor
+from oracle import truncate as tr
+
+
+# ---- test/test_cutruncate.jl:9-17 : three known-answer vectors ------------------------
+def test_truncate_kat1_zeros():
+    assert tr.truncate_gpu_reference(np.zeros(10)) == (0.0, 0.0, 1)
+    assert tr.truncate(np.zeros(10)) == (0.0, 0.0, 1)
+
+
+def test_truncate_kat2_absolute_cutoff():
+    for f, kw in ((tr.truncate_gpu_reference, dict(absoluteCutoff=True)),
+                  (tr.truncate, dict(use_absolute_cutoff=True))):
+        err, docut, n = f([1.0, 0.5, 0.1, 0.05], cutoff=0.2, **kw)
+        assert err == pytest.approx(0.15) and docut == pytest.approx(0.3) and n == 2
+
+
+def test_truncate_kat3_reference_value_and_cpu_rule():
+    # the reference's GPU code keeps 1 and reports docut 0.45 (test_cutruncate.jl:14-17) ...
+    err, docut, n = tr.truncate_gpu_reference([0.5, 0.4, 0.1], cutoff=0.2)
+    assert err == pytest.approx(0.1) and docut == pytest.approx(0.45) and n == 1
+    # ... the CPU rule (parity target) keeps 2: deliberate, documented mismatch
+    err, docut, n = tr.truncate([0.5, 0.4, 0.1], cutoff=0.2)
+    assert err == pytest.approx(0.1) and docut == pytest.approx(0.25) and n == 2
+
+
+def test_truncate_maxdim_binding():
+    err, docut, n = tr.truncate([0.4, 0.3, 0.2, 0.1], maxdim=2)
+    assert n == 2 and err == pytest.approx(0.3)
+    err_g, _, n_g = tr.truncate_gpu_reference([0.4, 0.3, 0.2, 0.1], maxdim=2)
+    assert n_g == 2 and err_g == pytest.approx(1.4)   # reference GPU quirk (SURVEY a15 iii)
+
+
+def test_truncate_mindim_and_single():
+    assert tr.truncate([0.7]) == (0.0, 0.35, 1)
+    err, docut, n = tr.truncate([0.5, 1e-20, 1e-21], cutoff=1e-10, mindim=2)
+    assert n == 2
+
+
+# ---- test/test_cuitensor.jl:105-112,125-130 : svd / qr invariants ---------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_svd_qr_invariants(dtype):
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((10, 12)).astype(dtype)
+    if dtype is np.complex128:
+        A = A + 1j * rng.standard_normal((10, 12))
+    U, S, V, spec = linalg.svd(A)
+    assert tensor.rel_err(U @ np.diag(S) @ V.T, A) < 1e-14
+    assert np.linalg.norm(U.conj().T @ U - np.eye(10)) < 1e-13
+    assert np.linalg.norm(V.conj().T @ V - np.eye(10)) < 1e-13
+    Q, R = linalg.qr(A.T)
+    assert tensor.rel_err(Q @ R, A.T) < 1e-14
+    assert np.linalg.norm(Q.conj().T @ Q - np.eye(10)) < 1e-13
+
+
+def test_eigen_descending_truncated():
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((9, 4))
+    rho = X @ X.T
+    D, U, spec = linalg.eigen(rho, maxdim=3)
+    assert len(D) == 3 and np.all(np.diff(D) <= 0)
+    assert np.linalg.norm(rho @ U - U * D[None, :]) < 1e-12
+    w = np.sort(np.linalg.eigvalsh(rho))[::-1]
+    assert spec.truncerr == pytest.approx(np.sum(w[3:]) / np.sum(w), abs=1e-13)
+
+
+# ---- test/test_cucontract.jl:170-196 : permutation matrix of contractions -------------
+def test_contract_output_order_and_permutations():
+    import itertools
+    rng = np.random.default_rng(9)
+    dims = dict(i=2, j=3, k=4, l=5)
+    for pa in itertools.permutations("ijk"):
+        for pb in itertools.permutations("jkl"):
+            A = rng.standard_normal([dims[x] for x in pa])
+            B = rng.standard_normal([dims[x] for x in pb])
+            C, lc = tensor.contract(A, pa, B, pb)
+            assert lc == ("i", "l")
+            ref = np.einsum("".join(pa) + "," + "".join(pb) + "->il", A, B)
+            assert tensor.rel_err(C, ref) < 1e-14
+
+
+# ---- test/test_cuiterativesolvers.jl:13-28 : davidson residual ------------------------
+@pytest.mark.parametrize("cplx_start", [False, True])
+def test_davidson_residual(cplx_start):
+    rng = np.random.default_rng(10)
+    d = 10
+    A = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+    M = A @ A.conj().T
+    v = rng.standard_normal(d) + (1j * rng.standard_normal(d) if cplx_start else 0)
+    lam, x = dmrg.davidson(lambda u: M @ u, v.astype(complex), maxiter=10)
+    assert np.linalg.norm(M @ x - lam * x) < 1e-6 * abs(lam) + 1e-8
+
+
+def test_lanczos_small_matrix_exact():
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((3, 3))
+    A = A + A.T
+    lam, x, nmv = dmrg.lanczos(lambda u: A @ u, rng.standard_normal(3), krylovdim=3)
+    assert nmv == 3 and lam == pytest.approx(np.linalg.eigvalsh(A)[0], abs=1e-12)
+
+
+# ---- test/test_cumps.jl:200-229 : orthogonality to 1e-12 -------------------------------
+def test_orthogonalize_gauge():
+    rng = np.random.default_rng(12)
+    psi = [rng.standard_normal((1 if j == 0 else 4, 2, 1 if j == 29 else 4)) for j in range(30)]
+    c = 14
+    out = mps.orthogonalize(psi, c)
+    for j in range(c):
+        assert mps.left_orthogonality_error(out[j]) < 1e-12
+    for j in range(c + 1, 30):
+        assert mps.right_orthogonality_error(out[j]) < 1e-12
+    assert abs(mps.inner(out, out) - mps.inner(psi, psi)) < 1e-10 * abs(mps.inner(psi, psi))
+
+
+# ---- test/dmrg.jl:5-29 : S=1 Heisenberg N=10, and ED -----------------------------------
+def test_dmrg_spin_one_heisenberg_vs_ed():
+    N = 10
+    Ws = models.heisenberg_mpo(N, 1.0)
+    psi0 = mps.random_mps(N, 3, 1, np.random.default_rng(2024))
+    sw = dmrg.Sweeps(3, maxdim=[10, 20, 40], mindim=[1, 10], cutoff=1e-11, noise=1e-10)
+    e, psi, hist = dmrg.dmrg(Ws, psi0, sw)
+    assert e < -12.0                                   # the reference's assertion
+    assert hist[1] <= hist[0] + 1e-9 and hist[2] <= hist[1] + 1e-9
+    e_ed = models.ed_ground_energy(Ws)
+    sw = dmrg.Sweeps(6, maxdim=[10, 20, 40, 80], cutoff=1e-12, noise=[1e-10, 1e-10, 0.0])
+    e, psi, _ = dmrg.dmrg(Ws, psi0, sw)
+    assert abs(e - e_ed) < 1e-8
+    assert abs(mps.expect_mpo(psi, Ws) / mps.inner(psi, psi) - e) < 1e-9
+
+
+# ---- test/dmrg.jl:58-81 : TFIM closed form ---------------------------------------------
+def test_dmrg_tfim_closed_form():
+    N = 32
+    Ws = models.tfim_mpo(N)
+    psi0 = mps.random_mps(N, 2, 1, np.random.default_rng(432))
+    sw = dmrg.Sweeps(5, maxdim=[10, 20], cutoff=1e-12, noise=1e-10)
+    e, _, _ = dmrg.dmrg(Ws, psi0, sw)
+    ex = models.tfim_exact_energy(N)
+    assert abs((e - ex) / ex) < 1e-2                   # the reference's assertion
+    assert abs((e - ex) / ex) < 1e-4
+
+
+# ---- examples/gate_evolution.jl : gate application --------------------------------------
+def test_apply_one_site_gates_and_two_site_exactness():
+    N = 6
+    psi = mps.product_mps(N, 2, [0] * N)
+    X = np.array([[0.0, 1.0], [1.0, 0.0]])
+    out, c = tebd.apply([(X, n) for n in range(N)], psi)
+    dense = mps.to_dense(out)
+    assert abs(dense[(1,) * N]) == pytest.approx(1.0)
+    rng = np.random.default_rng(13)
+    psi = mps.random_mps(N, 2, 8, rng)
+    G = models.heisenberg_bond_gate(0.05)
+    gates = tebd.tebd_layer_gates(N, G, 0) + tebd.tebd_layer_gates(N, G, 1)
+    out, c = tebd.apply(gates, psi, center=0, cutoff=1e-14)
+    want = mps.to_dense(psi)
+    for Gm, n in gates:
+        want = np.moveaxis(np.tensordot(Gm, want, axes=([2, 3], [n, n + 1])), [0, 1], [n, n + 1])
+    assert tensor.rel_err(mps.to_dense(out), want) < 1e-12
+
+
+def test_heff_matches_dense_hamiltonian():
+    N = 6
+    Ws = models.heisenberg_mpo(N, 0.5)
+    rng = np.random.default_rng(14)
+    psi = mps.random_mps(N, 2, 8, rng)
+    psi = mps.orthogonalize(psi, 2)
+    Rs = dmrg.build_right_envs(psi, Ws, upto=1)
+    L = np.ones((1, 1, 1))
+    for j in range(2):
+        L = dmrg.env_left_update(L, psi[j], Ws[j])
+    phi = np.tensordot(psi[2], psi[3], axes=(2, 0))
+    Hphi = dmrg.heff_apply(L, Ws[2], Ws[3], Rs[3], phi)
+    e_local = np.vdot(phi.ravel(), Hphi.ravel())
+    e_full = mps.expect_mpo(psi, Ws)
+    assert abs(e_local - e_full) < 1e-12
+    l, d, _, r = phi.shape
+    assert dmrg.heff_flops(l, r, d, 5) == 2 * d * d * 5 * (l * l * r + l * r * r) + 4 * d ** 3 * 25 * l * r
