@@ -1,0 +1,220 @@
+/*
+ * tnb200.h -- C ABI of libtnb200.so: the B200-native (sm_100a) replacement for the
+ * ITensorsGPU.jl hot path (dense ITensor contraction, H_eff*psi + eigensolver, truncated
+ * svd/eigen in replacebond!/factorize, TEBD gate step).
+ *
+ * The reference has no FFI of its own: it is Julia methods dispatched on `CuDense` storage
+ * that forward to cuTENSOR / cuBLAS / cuSOLVER (override surface = the import list at
+ * /root/reference/src/ITensorsGPU.jl:32-43).  Every entry point below names the reference
+ * method body it replaces (file:line relative to /root/reference).  INTEGRATION.md shows
+ * the Julia `ccall` stub for each one.
+ *
+ * Conventions
+ *   - Tensors are flat, dense, COLUMN-MAJOR device buffers over their mode order
+ *     (src/tensor/cudense.jl:252-254); complex is interleaved (re,im) = Julia ComplexF64.
+ *   - Modes are small non-negative ints; the same label in two operands of a contraction
+ *     means "contract", exactly like the mode numbering at src/tensor/cudense.jl:258-283.
+ *   - Caller owns every tensor buffer.  The library owns only the opaque handle
+ *     (workspace arena, plan cache -- the analogue of `ContractionPlans`,
+ *     src/ITensorsGPU.jl:54-55).  One handle per host thread; not thread-safe.
+ *   - All calls are asynchronous on `stream` unless they return a host scalar
+ *     (documented per function).  `stream` is a cudaStream_t passed as void*.
+ *   - Return value: 0 on success, a tnb_status otherwise; tnb_last_error() gives text.
+ *     Nothing here aborts the process and nothing falls back to the CPU.
+ */
+#ifndef TNB200_H
+#define TNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tnb_handle_s* tnb_handle_t;
+
+typedef enum {
+  TNB_OK = 0,
+  TNB_ERR_BAD_ARG = 1,        /* Julia side: ArgumentError      (src/mps/cumpo.jl:21)        */
+  TNB_ERR_DIM_MISMATCH = 2,   /* Julia side: DimensionMismatch  (src/cuitensor.jl:55,72,78)  */
+  TNB_ERR_UNSUPPORTED = 3,    /* Julia side: error(...)         (src/tensor/cudense.jl:165)  */
+  TNB_ERR_CUDA = 4,
+  TNB_ERR_NO_CONVERGENCE = 5,
+  TNB_ERR_ALLOC = 6
+} tnb_status;
+
+typedef enum { TNB_F64 = 0, TNB_C128 = 1 } tnb_dtype;
+
+/* flags for tnb_contract */
+#define TNB_CONJ_A 1
+#define TNB_CONJ_B 2
+
+/* flags for truncation (kwargs of truncate!, src/tensor/cutruncate.jl:3-7) */
+#define TNB_TRUNC_ABSOLUTE_CUTOFF 1   /* absoluteCutoff / use_absolute_cutoff */
+#define TNB_TRUNC_NO_RELATIVE     2   /* doRelCutoff=false / use_relative_cutoff=false */
+
+/* which_decomp for tnb_factorize ([EXT] ITensors factorize) */
+#define TNB_DECOMP_AUTO  0
+#define TNB_DECOMP_SVD   1
+#define TNB_DECOMP_EIGEN 2
+#define TNB_DECOMP_QR    3
+
+#define TNB_ORTHO_LEFT  0
+#define TNB_ORTHO_RIGHT 1
+
+/* ------------------------------------------------------------------ handle ------------ */
+int tnb_create(tnb_handle_t* out);            /* binds to the current CUDA device */
+int tnb_destroy(tnb_handle_t h);
+const char* tnb_last_error(tnb_handle_t h);
+int tnb_version(void);
+/* Pre-size the workspace arena (bytes).  Optional; the arena grows on demand (growing
+ * synchronises the device). */
+int tnb_reserve(tnb_handle_t h, size_t bytes);
+size_t tnb_workspace_bytes(tnb_handle_t h);
+/* Number of kernels this library has launched through the handle (bench `gpu_launches`). */
+uint64_t tnb_launch_count(tnb_handle_t h);
+
+/* ------------------------------------------------------------------ tier 1: primitives - */
+
+/* C[modeC] <- alpha * sum_{shared} A[modeA] * B[modeB] + beta * C[modeC]
+ * Replaces _contract! -> CUTENSOR.contraction!  (src/tensor/cudense.jl:238-331), the
+ * scalar/outer branches of contract!! (src/tensor/cudense.jl:83-110, 74-81, 129-168),
+ * the cuBLAS fallback _gemm_contract! (src/tensor/cudense.jl:170-236) and the alpha/beta
+ * form contract!!(...,alpha,beta) (src/tensor/dense.jl:1-48).
+ * alpha, beta: host pointers to one element of `dtype` (NULL = 1 and 0).
+ * A mode that appears in only one tensor, or in all three, is TNB_ERR_BAD_ARG.
+ * The index permutation is fused into the tile loads: no permuted copy is ever made. */
+int tnb_contract(tnb_handle_t h, int dtype,
+                 int nA, const int64_t* extA, const int32_t* modeA, const void* A,
+                 int nB, const int64_t* extB, const int32_t* modeB, const void* B,
+                 int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                 const void* alpha, const void* beta, int flags, void* stream);
+
+/* B[modeB] <- alpha * A[modeA] + beta * B[modeB]   (modeB is a permutation of modeA)
+ * Replaces permute!/permutedims!! -> CUTENSOR.permutation! (src/tensor/cudense.jl:447-500,
+ * 38-60, 112-127) and +/- -> CUTENSOR.elementwiseBinary! (src/tensor/cudense.jl:333-445):
+ * one fused pass instead of zeros + elementwiseBinary + copyto!. */
+int tnb_permute_axpby(tnb_handle_t h, int dtype, int n, const int64_t* extA,
+                      const int32_t* modeA, const void* A, const int32_t* modeB, void* B,
+                      const void* alpha, const void* beta, void* stream);
+
+/* x <- alpha * x       (scalar * and /: src/tensor/cudense.jl:22,502) */
+int tnb_scale(tnb_handle_t h, int dtype, int64_t n, void* x, const void* alpha, void* stream);
+
+/* result = sum conj(x_i) * y_i  -> device scalar `result_dev` (1 element of dtype); if
+ * result_host != NULL the call synchronises and also writes it there.
+ * Replaces dot = scalar(dag(A)*B) (contract to rank 0 + D2H: src/tensor/cudense.jl:25-26) */
+int tnb_dot(tnb_handle_t h, int dtype, int64_t n, const void* x, const void* y,
+            void* result_dev, void* result_host, void* stream);
+
+/* ||x||_2 -> device double; optional host copy (sync).  Replaces norm (cudense.jl:27). */
+int tnb_nrm2(tnb_handle_t h, int dtype, int64_t n, const void* x, double* result_dev,
+             double* result_host, void* stream);
+
+/* Spectrum truncation on a DEVICE vector of descending weights (CPU rule of [EXT] NDTensors
+ * truncate!; replaces truncate!(P::CuVector) src/tensor/cutruncate.jl:1-93 -- one kernel
+ * and one 24-byte readback instead of ~10 kernels and ~6 syncs).  Synchronises. */
+int tnb_truncate(tnb_handle_t h, const double* P_dev, int64_t len, int64_t maxdim,
+                 int64_t mindim, double cutoff, int flags, int64_t* n_keep,
+                 double* truncerr, double* docut, void* stream);
+
+/* Thin SVD with truncation of A (m x n, column-major, lda = m; destroyed).
+ * U (m x kmax), S (kmax), V (n x kmax) with A ~= U diag(S) V^T (CPU `conj!(MV)` convention),
+ * kmax = min(m,n,maxdim); *n_keep columns are valid.  Blocked one-sided Jacobi.
+ * Replaces svd(::CuDenseTensor{_,2}) -> CUSOLVER.svd! (src/tensor/culinearalgebra.jl:33-72).
+ * Synchronises (returns host scalars). */
+int tnb_svd_trunc(tnb_handle_t h, int dtype, int64_t m, int64_t n, void* A,
+                  int64_t maxdim, int64_t mindim, double cutoff, int flags, int do_truncate,
+                  void* U, double* S, void* V, int64_t* n_keep, double* truncerr,
+                  void* stream);
+
+/* Hermitian eigendecomposition, eigenvalues DEscending, truncated.  A (n x n, upper triangle
+ * referenced like syevd 'U'; destroyed).  D (kmax) device, U (n x kmax).
+ * Replaces eigen(::Hermitian{CuDenseTensor}) -> syevd!/heevd! + reverse + truncate!
+ * (src/tensor/culinearalgebra.jl:74-108).  Synchronises. */
+int tnb_eigh_trunc(tnb_handle_t h, int dtype, int64_t n, void* A, int64_t maxdim,
+                   int64_t mindim, double cutoff, int flags, int do_truncate, double* D,
+                   void* U, int64_t* n_keep, double* truncerr, void* stream);
+
+/* Thin QR with explicit Q: A (m x n) -> Q (m x k), R (k x n), k = min(m,n).  diag(R) >= 0.
+ * Replaces qr(::CuDenseTensor{_,2}) (src/tensor/culinearalgebra.jl:110-121). */
+int tnb_qr(tnb_handle_t h, int dtype, int64_t m, int64_t n, const void* A, void* Q, void* R,
+           void* stream);
+
+/* ------------------------------------------------------------------ tier 2: fused DMRG - */
+/* Fixed layouts (column-major): phi[l,s1,s2,r], L[l,l',a], R[r,r',c], W1[a,s1,s1',b],
+ * W2[b,s2,s2',c]; unprimed = ket side.  These replace sequences of primitive calls that
+ * [EXT] ITensors issues through the override surface; anchors are the reference call
+ * sites examples/dmrg.jl:25, test/dmrg.jl:27,75. */
+
+typedef struct {
+  int64_t chiL, chiR;   /* MPS bond dims left/right of the two sites */
+  int32_t d1, d2;       /* site dims */
+  int32_t wL, wM, wR;   /* MPO bond dims: left of site b, between, right of site b+1 */
+} tnb_bond_dims;
+
+/* out <- H_eff * phi = (((phi*L)*W1)*W2)*R   ([EXT] product(::ProjMPO, ::ITensor)); four
+ * contractions on persistent workspace, no allocation / zero-fill (replaces 4x
+ * src/tensor/cudense.jl:238-331 + 3x src/tensor/cudense.jl:62-72). */
+int tnb_heff_apply(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
+                   const void* W1, const void* W2, const void* R, const void* phi,
+                   void* out, void* stream);
+/* Same, phi and out in HOST memory (pinned or pageable): H2D + apply + D2H, synchronous.
+ * This is the end-to-end form timed by bench.py `e2e`. */
+int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
+                        const void* W1, const void* W2, const void* R, const void* phi_host,
+                        void* out_host, void* stream);
+
+/* Lnew[r,r',b] <- ((L*A)*W)*conj(A')  with A[l,s,r]  ([EXT] makeL!) */
+int tnb_env_update_left(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d,
+                        int32_t wL, int32_t wR, const void* L, const void* A, const void* W,
+                        void* Lnew, void* stream);
+/* Rnew[l,l',a] <- ((R*A)*W)*conj(A')  ([EXT] makeR!) */
+int tnb_env_update_right(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d,
+                         int32_t wL, int32_t wR, const void* R, const void* A, const void* W,
+                         void* Rnew, void* stream);
+
+/* Lowest eigenpair of H_eff by one Lanczos cycle with full re-orthogonalisation
+ * ([EXT] KrylovKit.eigsolve(PH, phi, 1, :SR; krylovdim, maxiter, tol)).  phi: in = start
+ * vector, out = normalised Ritz vector.  Krylov vectors and all scalars stay on the device;
+ * one readback at the end.  Synchronises. */
+int tnb_eigsolve_lanczos(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
+                         const void* W1, const void* W2, const void* R, void* phi,
+                         int krylovdim, int maxiter, double tol, double* energy,
+                         int* n_matvec, void* stream);
+
+/* rho_pert <- noise * nt*nt^dagger  ([EXT] noiseterm(::ProjMPO, phi, ortho)); rho_pert is
+ * (chiL*d1)^2 for ortho left, (d2*chiR)^2 for ortho right; accumulate=1 adds into it. */
+int tnb_noise_term(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
+                   const void* W1, const void* W2, const void* R, const void* phi, int ortho,
+                   double noise, int accumulate, void* rho, void* stream);
+
+/* Split phi[l,s1,s2,r] -> A[l,s1,k] * B[k,s2,r] with truncation, orthogonality side and
+ * normalisation ([EXT] replacebond! -> factorize; svd/eigen bodies at
+ * src/tensor/culinearalgebra.jl:33-108).  A, B sized for kmax = min(chiL*d1, d2*chiR, maxdim).
+ * rho_pert may be NULL.  Synchronises. */
+int tnb_factorize_bond(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, void* phi,
+                       int ortho, int which_decomp, int64_t maxdim, int64_t mindim,
+                       double cutoff, const void* rho_pert, int normalize, void* A, void* B,
+                       int64_t* n_keep, double* truncerr, void* stream);
+
+/* One full two-site DMRG bond update: phi = A1*A2; Lanczos; optional noise; factorize.
+ * A1/A2 are overwritten (buffers sized for kmax). */
+int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
+                       const void* W1, const void* W2, const void* R, void* A1, void* A2,
+                       int ortho, int which_decomp, int64_t maxdim, int64_t mindim,
+                       double cutoff, double noise, int krylovdim, int maxiter,
+                       double* energy, int64_t* n_keep, double* truncerr, void* stream);
+
+/* theta[l,s1',s2',r] <- sum G[s1',s2',s1,s2] A1[l,s1,k] A2[k,s2,r]  then left-orthogonal
+ * split with truncation ([EXT] apply / product(o, psi); examples/gate_evolution.jl:46). */
+int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR,
+                        int32_t d1, int32_t d2, const void* G, void* A1, void* A2,
+                        int64_t maxdim, int64_t mindim, double cutoff, int64_t* n_keep,
+                        double* truncerr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNB200_H */

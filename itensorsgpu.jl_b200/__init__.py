@@ -1,0 +1,12 @@
+"""itensorsgpu.jl_b200 -- B200-native (sm_100a) replacement for the ITensorsGPU.jl hot path.
+
+Only what the path needs: ``csrc/`` (CUDA kernels + the C ABI, built into
+``lib/libtnb200.so``), ``_lib`` (ctypes binding), ``ops`` (one host function per entry
+point on flat device tensors) and ``itensor`` (the host-side mirror of the reference's
+ITensor-level interface: ``cu``, ``cpu``, ``*``, ``+``, ``svd``, ``eigen``, ``qr``, ``dmrg``,
+``apply``).  The directory name is not an importable identifier; import it through the
+repo-root shim:  ``from itensorsgpu_b200 import tn``.
+"""
+from . import _lib, ops  # noqa: F401
+from ._lib import TnbError, DimensionMismatch, handle, load  # noqa: F401
+from .ops import DTensor  # noqa: F401

@@ -1,0 +1,132 @@
+"""ctypes binding of libtnb200.so (the C ABI declared in include/tnb200.h).
+
+The library is the product; this module only loads it and declares signatures.  There is
+no CPU fallback: if the shared object is missing or no sm_100 device is present, every
+entry point raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtnb200.so")
+
+F64, C128 = 0, 1
+CONJ_A, CONJ_B = 1, 2
+TRUNC_ABSOLUTE_CUTOFF, TRUNC_NO_RELATIVE = 1, 2
+DECOMP_AUTO, DECOMP_SVD, DECOMP_EIGEN, DECOMP_QR = 0, 1, 2, 3
+ORTHO_LEFT, ORTHO_RIGHT = 0, 1
+
+STATUS = {0: "OK", 1: "BAD_ARG", 2: "DIM_MISMATCH", 3: "UNSUPPORTED", 4: "CUDA", 5: "NO_CONVERGENCE", 6: "ALLOC"}
+
+
+class TnbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libtnb200: %s (%s)" % (msg, STATUS.get(code, code)))
+        self.code = code
+
+
+class DimensionMismatch(TnbError):
+    """Mirrors Julia's DimensionMismatch (reference src/cuitensor.jl:55,72,78)."""
+
+
+class BondDims(C.Structure):
+    _fields_ = [("chiL", C.c_int64), ("chiR", C.c_int64), ("d1", C.c_int32), ("d2", C.c_int32),
+                ("wL", C.c_int32), ("wM", C.c_int32), ("wR", C.c_int32)]
+
+
+_vp, _i64, _i32, _int, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_double
+_pi64, _pi32, _pdbl, _pint = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int)
+_pbd = C.POINTER(BondDims)
+
+# name -> (restype, argtypes); must list every symbol include/tnb200.h declares
+SIGNATURES = {
+    "tnb_create": (_int, [C.POINTER(_vp)]),
+    "tnb_destroy": (_int, [_vp]),
+    "tnb_last_error": (C.c_char_p, [_vp]),
+    "tnb_version": (_int, []),
+    "tnb_reserve": (_int, [_vp, C.c_size_t]),
+    "tnb_workspace_bytes": (C.c_size_t, [_vp]),
+    "tnb_launch_count": (C.c_uint64, [_vp]),
+    "tnb_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp,
+                            _vp, _vp, _int, _vp]),
+    "tnb_permute_axpby": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _pi32, _vp, _vp, _vp, _vp]),
+    "tnb_scale": (_int, [_vp, _int, _i64, _vp, _vp, _vp]),
+    "tnb_dot": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_nrm2": (_int, [_vp, _int, _i64, _vp, _vp, _pdbl, _vp]),
+    "tnb_truncate": (_int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _pi64, _pdbl, _pdbl, _vp]),
+    "tnb_svd_trunc": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _i64, _dbl, _int, _int, _vp, _vp, _vp, _pi64, _pdbl,
+                             _vp]),
+    "tnb_eigh_trunc": (_int, [_vp, _int, _i64, _vp, _i64, _i64, _dbl, _int, _int, _vp, _vp, _pi64, _pdbl, _vp]),
+    "tnb_qr": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "tnb_heff_apply": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_heff_apply_host": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_env_update_left": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_env_update_right": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_eigsolve_lanczos": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _int, _int, _dbl, _pdbl, _pint, _vp]),
+    "tnb_noise_term": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _int, _dbl, _int, _vp, _vp]),
+    "tnb_factorize_bond": (_int, [_vp, _int, _pbd, _vp, _int, _int, _i64, _i64, _dbl, _vp, _int, _vp, _vp, _pi64,
+                                  _pdbl, _vp]),
+    "tnb_dmrg_bond_step": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _i64, _dbl, _dbl,
+                                  _int, _int, _pdbl, _pi64, _pdbl, _vp]),
+    "tnb_tebd_apply_gate": (_int, [_vp, _int, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _dbl, _pi64,
+                                   _pdbl, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the shared library and attach signatures.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libtnb200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(expected at %s).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Handle:
+    """Owns one tnb_handle_t bound to the current CUDA device."""
+
+    def __init__(self):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.tnb_create(C.byref(h))
+        if rc != 0:
+            raise TnbError(rc, "tnb_create failed: a B200 (sm_100) device is required; no CPU fallback")
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.tnb_last_error(self.h).decode()
+            raise (DimensionMismatch if rc == 2 else TnbError)(rc, msg)
+
+    def close(self):
+        if self.h:
+            self.lib.tnb_destroy(self.h)
+            self.h = None
+
+    @property
+    def launches(self):
+        return int(self.lib.tnb_launch_count(self.h))
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.tnb_workspace_bytes(self.h))
+
+
+_handle = None
+
+
+def handle():
+    global _handle
+    if _handle is None:
+        _handle = Handle()
+    return _handle

@@ -1,0 +1,571 @@
+// Dense tensor contraction on FP64 / complex-FP64 DMMA tiles with the index permutation
+// fused into the tile loads (GETT-style: no permuted copy of any operand is ever made).
+//
+// Replaces `_contract!` -> CUTENSOR.contraction! (/root/reference/src/tensor/cudense.jl:238-331),
+// `_gemm_contract!` (cudense.jl:170-236) and the scalar/outer branches of `contract!!`
+// (cudense.jl:83-110).
+//
+// Design (sm_100a): tcgen05/UMMA has no f64 kind, so FP64 tensor math is warp-level
+// `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4).  One CTA owns a BM x BN tile of the
+// "matricised" C; modes are grouped into M (A&C), N (B&C), K (A&B), each group linearised
+// in mixed radix, so element (m,k) of A lives at offM_A(m) + offK_A(k).  Tiles are staged
+// global->shared with a 4-deep cp.async (LDGSTS) ring, each operand along whichever of its
+// two directions is contiguous in HBM (16-byte copies when parity allows), into a padded
+// layout that makes the 64-bit fragment loads bank-conflict free.
+#include "tnb_internal.h"
+
+#include <algorithm>
+#include <array>
+#include <cstring>
+
+namespace tnb {
+
+// ------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------
+template <bool USE_Y>
+__device__ __forceinline__ long long decode(const Group& g, int idx) {
+  long long off = 0;
+  const int n1 = g.n - 1;
+#pragma unroll 1
+  for (int i = 0; i < n1; ++i) {
+    const int e = g.ext[i];
+    const int q = idx / e;
+    const int r = idx - q * e;
+    off += (long long)r * (USE_Y ? g.sY[i] : g.sX[i]);
+    idx = q;
+  }
+  off += (long long)idx * (USE_Y ? g.sY[n1] : g.sX[n1]);
+  return off;
+}
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* g, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(g), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(g), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor op.  Lane l holds A[l/4][l%4],
+// B[l%4][l/4], C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_>
+struct Cfg {
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int NT = WARPS_M * WARPS_N * 32;
+  static constexpr int MI = WM / 8, NI = WN / 8;
+};
+
+// Shared-memory geometry of one operand tile (ROWS free-dim entries x BK), in elements.
+// K-major  : [row][k], pitch PK  (contiguous direction in HBM is k)
+// free-major: [k][row], pitch PR (contiguous direction in HBM is the free index)
+// Pitches chosen so a half-warp's 64-bit (quarter-warp's 128-bit) fragment loads hit
+// distinct banks: real  PK%16==4, PR%16==4 ; complex PK%8==4, PR%8==2.
+template <bool CPLX, int ROWS, int BK>
+struct TileGeom {
+  static constexpr int PK = BK + 4;
+  static constexpr int PR = ROWS + (CPLX ? 2 : 4);
+  static constexpr int ELEMS_K = ROWS * PK;
+  static constexpr int ELEMS_R = BK * PR;
+  static constexpr int ELEMS = ELEMS_K > ELEMS_R ? ELEMS_K : ELEMS_R;
+};
+
+// Issue the cp.async copies of one operand tile.  `rowoff` are this thread's precomputed
+// free-index offsets (CONTIG_K: one per pass; CONTIG_R: one in total), `rowok` their masks.
+template <bool CPLX, bool CONTIG_K, int VEC, int ROWS, int BK, int NT, bool KY>
+struct Loader {
+  using G = TileGeom<CPLX, ROWS, BK>;
+  static constexpr int EB = CPLX ? 16 : 8;
+  static constexpr int VPR = BK / VEC;                       // CONTIG_K: vectors per row
+  static constexpr int RPP = NT / VPR;                       //           rows per pass
+  static constexpr int VPK = ROWS / VEC;                     // CONTIG_R: vectors per k-row
+  static constexpr int KPP = NT / VPK;                       //           k-rows per pass
+  static constexpr int NPASS = CONTIG_K ? (ROWS / RPP) : (BK / KPP);
+  static constexpr int NROW = CONTIG_K ? NPASS : 1;
+  static_assert(NT % (CONTIG_K ? VPR : VPK) == 0, "thread mapping");
+  static_assert(NPASS >= 1, "tile too small for the CTA");
+
+  long long rowoff[NROW];
+  bool rowok[NROW];
+
+  __device__ __forceinline__ void init(const Group& g, int row0, int R, int tid) {
+    if (CONTIG_K) {
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        int r = row0 + tid / VPR + i * RPP;
+        rowok[i] = r < R;
+        rowoff[i] = rowok[i] ? decode<false>(g, r) : 0;
+      }
+    } else {
+      int r = row0 + (tid % VPK) * VEC;
+      rowok[0] = r < R;
+      rowoff[0] = rowok[0] ? decode<false>(g, r) : 0;
+    }
+  }
+
+  __device__ __forceinline__ void issue(const char* base, char* smem, const Group& gk, int k0,
+                                        int K, int tid) const {
+    if (CONTIG_K) {
+      const int kv = (tid % VPR) * VEC;
+      const int k = k0 + kv;
+      const bool kok = k < K;
+      const long long koff = kok ? decode<KY>(gk, k) : 0;
+      const int r = tid / VPR;
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        char* dst = smem + (size_t)((r + i * RPP) * G::PK + kv) * EB;
+        const bool ok = kok && rowok[i];
+        const char* src = base + (ok ? (rowoff[i] + koff) * EB : 0);
+        if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
+      }
+    } else {
+      const int rv = (tid % VPK) * VEC;
+      const int kb = tid / VPK;
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        const int kl = kb + i * KPP;
+        const int k = k0 + kl;
+        const bool ok = rowok[0] && (k < K);
+        const long long koff = ok ? decode<KY>(gk, k) : 0;
+        char* dst = smem + (size_t)(kl * G::PR + rv) * EB;
+        const char* src = base + (ok ? (rowoff[0] + koff) * EB : 0);
+        if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------
+template <bool CPLX, bool AK, bool BKM, int VA, int VB, class CFG>
+__global__ void __launch_bounds__(CFG::NT, 1) contract_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int BM = CFG::BM, BN = CFG::BN, BK = CFG::BK, NT = CFG::NT, ST = CFG::STAGES;
+  constexpr int MI = CFG::MI, NI = CFG::NI;
+  constexpr int EB = CPLX ? 16 : 8;
+  using GA = TileGeom<CPLX, BM, BK>;
+  using GB = TileGeom<CPLX, BN, BK>;
+  constexpr int A_BYTES = GA::ELEMS * EB, B_BYTES = GB::ELEMS * EB;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp % CFG::WARPS_M) * CFG::WM;
+  const int wn0 = (warp / CFG::WARPS_M) * CFG::WN;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  // grouped rasterisation: GROUP_M consecutive row-tiles share each B panel in L2
+  int tm, tn;
+  {
+    const int t = blockIdx.x;
+    const int per_group = p.groupM * p.tilesN;
+    const int g = t / per_group;
+    const int first = g * p.groupM;
+    const int gsz = min(p.tilesM - first, p.groupM);
+    const int w = t - g * per_group;
+    tm = first + w % gsz;
+    tn = w / gsz;
+  }
+  const int m0 = tm * BM, n0 = tn * BN;
+
+  Loader<CPLX, AK, VA, BM, BK, NT, false> la;
+  Loader<CPLX, BKM, VB, BN, BK, NT, true> lb;
+  la.init(p.gm, m0, p.M, tid);
+  lb.init(p.gn, n0, p.N, tid);
+
+  const char* Ab = (const char*)p.A;
+  const char* Bb = (const char*)p.B;
+  const int KT = (p.K + BK - 1) / BK;
+
+  double acc[MI][NI][CPLX ? 4 : 2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+      for (int e = 0; e < (CPLX ? 4 : 2); ++e) acc[i][j][e] = 0.0;
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < ST - 1; ++s) {
+    if (s < KT) {
+      la.issue(Ab, (char*)smem + s * STAGE_BYTES, p.gk, s * BK, p.K, tid);
+      lb.issue(Bb, (char*)smem + s * STAGE_BYTES + A_BYTES, p.gk, s * BK, p.K, tid);
+    }
+    cp_async_commit();
+  }
+
+  const double sa = p.conjA ? -1.0 : 1.0, sb = p.conjB ? -1.0 : 1.0;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<ST - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + ST - 1;
+      if (nk < KT) {
+        const int s = nk % ST;
+        la.issue(Ab, (char*)smem + s * STAGE_BYTES, p.gk, nk * BK, p.K, tid);
+        lb.issue(Bb, (char*)smem + s * STAGE_BYTES + A_BYTES, p.gk, nk * BK, p.K, tid);
+      }
+      cp_async_commit();
+    }
+    const unsigned char* sA = smem + (kt % ST) * STAGE_BYTES;
+    const unsigned char* sB = sA + A_BYTES;
+    if (!CPLX) {
+      const double* As = (const double*)sA;
+      const double* Bs = (const double*)sB;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[MI], b[NI];
+        const int k = kk * 4 + lc;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int r = wm0 + i * 8 + lr;
+          a[i] = AK ? As[r * GA::PK + k] : As[k * GA::PR + r];
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int r = wn0 + j * 8 + lr;
+          b[j] = BKM ? Bs[r * GB::PK + k] : Bs[k * GB::PR + r];
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    } else {
+      const double2* As = (const double2*)sA;
+      const double2* Bs = (const double2*)sB;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double2 a[MI], b[NI];
+        const int k = kk * 4 + lc;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int r = wm0 + i * 8 + lr;
+          a[i] = AK ? As[r * GA::PK + k] : As[k * GA::PR + r];
+          a[i].y *= sa;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int r = wn0 + j * 8 + lr;
+          b[j] = BKM ? Bs[r * GB::PK + k] : Bs[k * GB::PR + r];
+          b[j].y *= sb;
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const double nai = -a[i].y;
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+            dmma(acc[i][j][0], acc[i][j][1], nai, b[j].y);
+            dmma(acc[i][j][2], acc[i][j][3], a[i].x, b[j].y);
+            dmma(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: direct stores from the accumulator fragments (8 consecutive m per quad-column
+  // -> full 32-byte sectors when C is M-major, which is the NDTensors output order).
+  long long offm[MI];
+  bool okm[MI];
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    const int m = m0 + wm0 + i * 8 + lr;
+    okm[i] = m < p.M;
+    offm[i] = okm[i] ? decode<true>(p.gm, m) : 0;
+  }
+  const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = n0 + wn0 + j * 8 + lc * 2 + e;
+      if (n >= p.N) continue;
+      const long long offn = decode<true>(p.gn, n);
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        if (!okm[i]) continue;
+        if (!CPLX) {
+          double* c = (double*)p.C + offm[i] + offn;
+          double v = p.alpha_re * acc[i][j][e];
+          if (has_beta) v += p.beta_re * (*c);
+          *c = v;
+        } else {
+          double2* c = (double2*)p.C + offm[i] + offn;
+          const double xr = acc[i][j][e], xi = acc[i][j][2 + e];
+          double2 v;
+          v.x = p.alpha_re * xr - p.alpha_im * xi;
+          v.y = p.alpha_re * xi + p.alpha_im * xr;
+          if (has_beta) {
+            const double2 o = *c;
+            v.x += p.beta_re * o.x - p.beta_im * o.y;
+            v.y += p.beta_re * o.y + p.beta_im * o.x;
+          }
+          *c = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side: launch
+// ------------------------------------------------------------------------------------
+using CfgR = Cfg<128, 128, 16, 32, 64, 4>;   // real:    8 warps, warp tile 32x64
+using CfgRS = Cfg<64, 64, 16, 32, 32, 4>;    // real, small problems: 4 warps, 32x32
+using CfgC = Cfg<128, 64, 8, 32, 32, 4>;     // complex: 8 warps, warp tile 32x32
+using CfgCS = Cfg<64, 32, 8, 32, 16, 4>;     // complex small: 4 warps
+
+template <bool CPLX, class CFG>
+constexpr int smem_bytes() {
+  return CFG::STAGES * (TileGeom<CPLX, CFG::BM, CFG::BK>::ELEMS + TileGeom<CPLX, CFG::BN, CFG::BK>::ELEMS) *
+         (CPLX ? 16 : 8);
+}
+
+template <bool CPLX, bool AK, bool BKM, int VA, int VB, class CFG>
+static int launch_one(Handle* h, GemmParams& p, cudaStream_t st) {
+  auto kern = contract_kernel<CPLX, AK, BKM, VA, VB, CFG>;
+  constexpr int SM = smem_bytes<CPLX, CFG>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+    attr_done = true;
+  }
+  p.tilesM = (p.M + CFG::BM - 1) / CFG::BM;
+  p.tilesN = (p.N + CFG::BN - 1) / CFG::BN;
+  p.groupM = 16;
+  const long long tiles = (long long)p.tilesM * p.tilesN;
+  if (tiles > 2147483647LL) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: too many tiles");
+  kern<<<(unsigned)tiles, CFG::NT, SM, st>>>(p);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "contract_kernel launch");
+}
+
+template <bool CPLX, class CFG>
+static int launch_cfg(Handle* h, GemmParams& p, bool ak, bool bk, int va, int vb, cudaStream_t st) {
+  if (CPLX) { va = 1; vb = 1; }
+#define TNB_L(AKv, BKv, VAv, VBv) return launch_one<CPLX, AKv, BKv, CPLX ? 1 : VAv, CPLX ? 1 : VBv, CFG>(h, p, st)
+  if (ak) {
+    if (bk) {
+      if (va == 2) { if (vb == 2) TNB_L(true, true, 2, 2); else TNB_L(true, true, 2, 1); }
+      else         { if (vb == 2) TNB_L(true, true, 1, 2); else TNB_L(true, true, 1, 1); }
+    } else {
+      if (va == 2) { if (vb == 2) TNB_L(true, false, 2, 2); else TNB_L(true, false, 2, 1); }
+      else         { if (vb == 2) TNB_L(true, false, 1, 2); else TNB_L(true, false, 1, 1); }
+    }
+  } else {
+    if (bk) {
+      if (va == 2) { if (vb == 2) TNB_L(false, true, 2, 2); else TNB_L(false, true, 2, 1); }
+      else         { if (vb == 2) TNB_L(false, true, 1, 2); else TNB_L(false, true, 1, 1); }
+    } else {
+      if (va == 2) { if (vb == 2) TNB_L(false, false, 2, 2); else TNB_L(false, false, 2, 1); }
+      else         { if (vb == 2) TNB_L(false, false, 1, 2); else TNB_L(false, false, 1, 1); }
+    }
+  }
+#undef TNB_L
+}
+
+static bool all_even(const long long* s, int from, int n) {
+  for (int i = from; i < n; ++i)
+    if (s[i] & 1) return false;
+  return true;
+}
+
+// Decide per-operand staging direction and copy width, pick a tile config, launch.
+static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) {
+  const bool cplx = dtype == TNB_C128;
+  // A: contiguous along K if the first K mode has unit stride in A; along M if the first M mode has.
+  bool ak, bk;
+  int va = 1, vb = 1;
+  const bool a_k1 = p.gk.sX[0] == 1 && p.K > 1, a_m1 = p.gm.sX[0] == 1 && p.M > 1;
+  const bool b_k1 = p.gk.sY[0] == 1 && p.K > 1, b_n1 = p.gn.sX[0] == 1 && p.N > 1;
+  ak = a_k1 || !a_m1;
+  bk = b_k1 || !b_n1;
+  if (!cplx) {
+    if (a_k1) {
+      if ((p.gk.ext[0] % 2 == 0) && all_even(p.gk.sX, 1, p.gk.n) && all_even(p.gm.sX, 0, p.gm.n) &&
+          ((uintptr_t)p.A % 16 == 0)) va = 2;
+    } else if (a_m1) {
+      if ((p.gm.ext[0] % 2 == 0) && all_even(p.gm.sX, 1, p.gm.n) && all_even(p.gk.sX, 0, p.gk.n) &&
+          ((uintptr_t)p.A % 16 == 0)) va = 2;
+    }
+    if (b_k1) {
+      if ((p.gk.ext[0] % 2 == 0) && all_even(p.gk.sY, 1, p.gk.n) && all_even(p.gn.sX, 0, p.gn.n) &&
+          ((uintptr_t)p.B % 16 == 0)) vb = 2;
+    } else if (b_n1) {
+      if ((p.gn.ext[0] % 2 == 0) && all_even(p.gn.sX, 1, p.gn.n) && all_even(p.gk.sY, 0, p.gk.n) &&
+          ((uintptr_t)p.B % 16 == 0)) vb = 2;
+    }
+  }
+  // tile config: big tiles unless they cannot fill the machine
+  auto ntiles = [&](int bm, int bn) { return ((long long)(p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn); };
+  if (!cplx) {
+    const bool small = ntiles(CfgR::BM, CfgR::BN) < h->num_sms || p.M <= 64 || p.N <= 64;
+    if (small) return launch_cfg<false, CfgRS>(h, p, ak, bk, va, vb, st);
+    return launch_cfg<false, CfgR>(h, p, ak, bk, va, vb, st);
+  } else {
+    const bool small = ntiles(CfgC::BM, CfgC::BN) < h->num_sms || p.M <= 64 || p.N <= 32;
+    if (small) return launch_cfg<true, CfgCS>(h, p, ak, bk, va, vb, st);
+    return launch_cfg<true, CfgC>(h, p, ak, bk, va, vb, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side: planning from mode labels
+// ------------------------------------------------------------------------------------
+struct ModeRec {
+  int label;
+  long long ext, sA, sB, sC;
+  int posA, posB, posC;
+};
+
+static void finish_group(Group& g, std::vector<ModeRec>& ms, int which /*0=M,1=N,2=K*/) {
+  // drop extent-1 modes, merge modes adjacent in both carrying tensors
+  std::vector<std::array<long long, 3>> v;  // ext, sX, sY
+  for (auto& m : ms) {
+    if (m.ext == 1) continue;
+    long long sx = which == 1 ? m.sB : m.sA;
+    long long sy = which == 2 ? m.sB : m.sC;
+    if (!v.empty() && v.back()[1] * v.back()[0] == sx && v.back()[2] * v.back()[0] == sy &&
+        v.back()[0] * m.ext < 2147483647LL) {
+      v.back()[0] *= m.ext;
+    } else {
+      v.push_back({m.ext, sx, sy});
+    }
+  }
+  if (v.empty()) v.push_back({1, 0, 0});
+  g.n = (int)v.size();
+  for (int i = 0; i < g.n; ++i) {
+    g.ext[i] = (int)v[i][0];
+    g.sX[i] = v[i][1];
+    g.sY[i] = v[i][2];
+  }
+}
+
+static void set_scalars(GemmParams& p, int dtype, const void* alpha, const void* beta) {
+  p.alpha_re = 1.0; p.alpha_im = 0.0; p.beta_re = 0.0; p.beta_im = 0.0;
+  if (alpha) { p.alpha_re = ((const double*)alpha)[0]; if (dtype == TNB_C128) p.alpha_im = ((const double*)alpha)[1]; }
+  if (beta) { p.beta_re = ((const double*)beta)[0]; if (dtype == TNB_C128) p.beta_im = ((const double*)beta)[1]; }
+}
+
+int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
+                  const void* A, int nB, const int64_t* extB, const int32_t* modeB,
+                  const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                  const void* alpha, const void* beta, int flags, cudaStream_t st) {
+  if (dtype != TNB_F64 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: dtype %d", dtype);
+  if (nA < 0 || nB < 0 || nC < 0 || nA > 64 || nB > 64 || nC > 64)
+    return set_err(h, TNB_ERR_BAD_ARG, "contract: bad rank");
+  if (!A || !B || !C) return set_err(h, TNB_ERR_BAD_ARG, "contract: null tensor pointer");
+  std::vector<ModeRec> recs;
+  auto find = [&](int label) -> ModeRec* {
+    for (auto& r : recs) if (r.label == label) return &r;
+    return nullptr;
+  };
+  long long s = 1;
+  for (int i = 0; i < nA; ++i) {
+    if (find(modeA[i])) return set_err(h, TNB_ERR_BAD_ARG, "contract: repeated mode %d in A", modeA[i]);
+    if (extA[i] < 1) return set_err(h, TNB_ERR_BAD_ARG, "contract: extent < 1 in A");
+    recs.push_back({modeA[i], extA[i], s, 0, 0, i, -1, -1});
+    s *= extA[i];
+  }
+  s = 1;
+  for (int i = 0; i < nB; ++i) {
+    for (int j = 0; j < i; ++j) if (modeB[j] == modeB[i]) return set_err(h, TNB_ERR_BAD_ARG, "contract: repeated mode %d in B", modeB[i]);
+    if (extB[i] < 1) return set_err(h, TNB_ERR_BAD_ARG, "contract: extent < 1 in B");
+    ModeRec* r = find(modeB[i]);
+    if (r) {
+      if (r->ext != extB[i]) return set_err(h, TNB_ERR_DIM_MISMATCH, "contract: mode %d has extent %lld in A, %lld in B", modeB[i], r->ext, (long long)extB[i]);
+      r->sB = s; r->posB = i;
+    } else {
+      recs.push_back({modeB[i], extB[i], 0, s, 0, -1, i, -1});
+    }
+    s *= extB[i];
+  }
+  s = 1;
+  for (int i = 0; i < nC; ++i) {
+    for (int j = 0; j < i; ++j) if (modeC[j] == modeC[i]) return set_err(h, TNB_ERR_BAD_ARG, "contract: repeated mode %d in C", modeC[i]);
+    ModeRec* r = find(modeC[i]);
+    if (!r) return set_err(h, TNB_ERR_BAD_ARG, "contract: output mode %d is in neither input", modeC[i]);
+    if (r->ext != extC[i]) return set_err(h, TNB_ERR_DIM_MISMATCH, "contract: mode %d has extent %lld in C", modeC[i], (long long)extC[i]);
+    r->sC = s; r->posC = i;
+    s *= extC[i];
+  }
+  std::vector<ModeRec> gm, gn, gk;
+  for (auto& r : recs) {
+    const bool a = r.posA >= 0, b = r.posB >= 0, c = r.posC >= 0;
+    if (a && b && c) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: batch mode %d (in A, B and C)", r.label);
+    if (a && b) gk.push_back(r);
+    else if (a && c) gm.push_back(r);
+    else if (b && c) gn.push_back(r);
+    else return set_err(h, TNB_ERR_BAD_ARG, "contract: mode %d appears in only one tensor", r.label);
+  }
+  // orders: M follows A (= C for the NDTensors output order), N follows B, K follows the
+  // operand whose unit-stride mode is contracted (A first).
+  std::sort(gm.begin(), gm.end(), [](const ModeRec& x, const ModeRec& y) { return x.posA < y.posA; });
+  std::sort(gn.begin(), gn.end(), [](const ModeRec& x, const ModeRec& y) { return x.posB < y.posB; });
+  bool k_by_b = false;
+  if (!gk.empty()) {
+    bool a_first_in_k = false, b_first_in_k = false;
+    for (auto& r : gk) { if (r.sA == 1 && r.ext > 1) a_first_in_k = true; if (r.sB == 1 && r.ext > 1) b_first_in_k = true; }
+    k_by_b = !a_first_in_k && b_first_in_k;
+  }
+  if (k_by_b) std::sort(gk.begin(), gk.end(), [](const ModeRec& x, const ModeRec& y) { return x.posB < y.posB; });
+  else std::sort(gk.begin(), gk.end(), [](const ModeRec& x, const ModeRec& y) { return x.posA < y.posA; });
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  finish_group(p.gm, gm, 0);
+  finish_group(p.gn, gn, 1);
+  finish_group(p.gk, gk, 2);
+  if (p.gm.n > MAXG || p.gn.n > MAXG || p.gk.n > MAXG) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: more than %d unmergeable modes in a group", MAXG);
+  auto total = [&](const Group& g, long long& out) { out = 1; for (int i = 0; i < g.n; ++i) out *= g.ext[i]; return out <= 2147483647LL; };
+  long long M, N, K;
+  if (!total(p.gm, M) || !total(p.gn, N) || !total(p.gk, K)) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: grouped extent exceeds 2^31-1");
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.A = A; p.B = B; p.C = C;
+  set_scalars(p, dtype, alpha, beta);
+  p.conjA = (flags & TNB_CONJ_A) ? 1 : 0;
+  p.conjB = (flags & TNB_CONJ_B) ? 1 : 0;
+  return launch_planned(h, dtype, p, st);
+}
+
+int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
+              const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
+              const void* beta, void* C, int64_t ldc, cudaStream_t st) {
+  if (m == 0 || n == 0) return TNB_OK;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.gm.n = p.gn.n = p.gk.n = 1;
+  p.gm.ext[0] = (int)m; p.gn.ext[0] = (int)n; p.gk.ext[0] = (int)std::max<int64_t>(k, 1);
+  p.gm.sX[0] = (opA == 'N') ? 1 : lda;  p.gk.sX[0] = (opA == 'N') ? lda : 1;
+  p.gn.sX[0] = (opB == 'N') ? ldb : 1;  p.gk.sY[0] = (opB == 'N') ? 1 : ldb;
+  p.gm.sY[0] = 1; p.gn.sY[0] = ldc;
+  p.M = (int)m; p.N = (int)n; p.K = (int)std::max<int64_t>(k, 1);
+  p.A = A; p.B = B; p.C = C;
+  set_scalars(p, dtype, alpha, beta);
+  if (k == 0) { p.alpha_re = 0; p.alpha_im = 0; p.gk.sX[0] = 0; p.gk.sY[0] = 0; }
+  p.conjA = opA == 'C'; p.conjB = opB == 'C';
+  return launch_planned(h, dtype, p, st);
+}
+
+}  // namespace tnb

@@ -1,0 +1,445 @@
+// Tier 2: fused DMRG entry points built on the contraction kernel -- H_eff*phi, environment
+// updates, device-resident Lanczos, noise term.
+//
+// These replace the *sequences* of primitive calls that [EXT] ITensors.jl issues through the
+// reference's override surface (/root/reference/src/ITensorsGPU.jl:32-43) for
+// `product(::ProjMPO, ::ITensor)`, `makeL!/makeR!`, `KrylovKit.eigsolve` and `noiseterm`;
+// reference call sites: examples/dmrg.jl:25, test/dmrg.jl:27,75.  Compared with the
+// reference path there is no per-contraction allocation + zero fill
+// (src/tensor/cudense.jl:62-72), no descriptor/plan rebuild per call (cudense.jl:255-294)
+// and no blocking D2H per dot/norm (cudense.jl:25-27): temporaries live in the handle's
+// arena and every Lanczos scalar stays on the device until one final readback.
+#include "tnb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace tnb {
+
+enum { mL = 0, mS1, mS2, mR, mLp, mA, mS1p, mB, mS2p, mC, mRp, mLpp, mS1pp, mS2pp, mRpp };
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static size_t heff_ws_bytes(int dtype, const tnb_bond_dims* d) {
+  const size_t base = (size_t)d->chiL * d->chiR * d->d1 * d->d2;
+  const size_t w = std::max({d->wL, d->wM, d->wR});
+  return 2 * al256(base * w * elsize(dtype));
+}
+
+// out <- (((phi*L)*W1)*W2)*R using two ping-pong temporaries t0,t1 (each base*max(w) elements)
+static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                     const void* W2, const void* R, const void* phi, void* out, void* t0, void* t1,
+                     cudaStream_t st) {
+  const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
+  {  // 1. T1[s1,s2,r,l',a] = phi[l,s1,s2,r] L[l,l',a]
+    int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
+    int64_t eb[] = {cl, cl, wl};     int32_t mb[] = {mL, mLp, mA};
+    int64_t ec[] = {d1, d2, cr, cl, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
+    TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+  }
+  {  // 2. T2[s2,r,l',s1',b] = T1 W1[a,s1,s1',b]
+    int64_t ea[] = {d1, d2, cr, cl, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
+    int64_t eb[] = {wl, d1, d1, wm};     int32_t mb[] = {mA, mS1, mS1p, mB};
+    int64_t ec[] = {d2, cr, cl, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
+    TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W1, 5, ec, mc, t1, nullptr, nullptr, 0, st));
+  }
+  {  // 3. T3[r,l',s1',s2',c] = T2 W2[b,s2,s2',c]
+    int64_t ea[] = {d2, cr, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
+    int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
+    int64_t ec[] = {cr, cl, d1, d2, wr}; int32_t mc[] = {mR, mLp, mS1p, mS2p, mC};
+    TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 4, eb, mb, W2, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+  }
+  {  // 4. out[l',s1',s2',r'] = T3 R[r,r',c]
+    int64_t ea[] = {cr, cl, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t eb[] = {cr, cr, wr};         int32_t mb[] = {mR, mRp, mC};
+    int64_t ec[] = {cl, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
+    TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 3, eb, mb, R, 4, ec, mc, out, nullptr, nullptr, 0, st));
+  }
+  return TNB_OK;
+}
+
+static int check_dims(Handle* h, const tnb_bond_dims* d) {
+  if (!d) return set_err(h, TNB_ERR_BAD_ARG, "null dims");
+  if (d->chiL < 1 || d->chiR < 1 || d->d1 < 1 || d->d2 < 1 || d->wL < 1 || d->wM < 1 || d->wR < 1)
+    return set_err(h, TNB_ERR_BAD_ARG, "bond dims must be >= 1");
+  return TNB_OK;
+}
+
+int heff_apply_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                    const void* W2, const void* R, const void* phi, void* out, cudaStream_t st) {
+  TNB_TRY(check_dims(h, d));
+  ws_reset(h);
+  const size_t need = heff_ws_bytes(dtype, d);
+  TNB_TRY(ws_require(h, need));
+  void *t0, *t1;
+  TNB_TRY(ws_alloc(h, need / 2, &t0));
+  TNB_TRY(ws_alloc(h, need / 2, &t1));
+  return heff_core(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
+}
+
+// ------------------------------------------------------------------------------------
+// environment updates
+// ------------------------------------------------------------------------------------
+int env_update_impl(Handle* h, int dtype, bool left, int64_t cl, int64_t cr, int32_t d_, int32_t wl_,
+                    int32_t wr_, const void* E, const void* A, const void* W, void* Enew, cudaStream_t st) {
+  const int64_t d = d_, wl = wl_, wr = wr_;
+  if (cl < 1 || cr < 1 || d < 1 || wl < 1 || wr < 1) return set_err(h, TNB_ERR_BAD_ARG, "env_update: dims");
+  ws_reset(h);
+  const size_t es = elsize(dtype);
+  const size_t n1 = al256((size_t)cl * cr * d * std::max(wl, wr) * es);
+  TNB_TRY(ws_require(h, 2 * n1));
+  void *t0, *t1;
+  TNB_TRY(ws_alloc(h, n1, &t0));
+  TNB_TRY(ws_alloc(h, n1, &t1));
+  // labels: l, l', a, s, r, s', b, r'
+  enum { l = 0, lp, a, s, r, sp, b, rp };
+  if (left) {
+    {  // T1[l',a,s,r] = L[l,l',a] A[l,s,r]
+      int64_t ea[] = {cl, cl, wl}; int32_t ma[] = {l, lp, a};
+      int64_t eb[] = {cl, d, cr};  int32_t mb[] = {l, s, r};
+      int64_t ec[] = {cl, wl, d, cr}; int32_t mc[] = {lp, a, s, r};
+      TNB_TRY(contract_impl(h, dtype, 3, ea, ma, E, 3, eb, mb, A, 4, ec, mc, t0, nullptr, nullptr, 0, st));
+    }
+    {  // T2[l',r,s',b] = T1 W[a,s,s',b]
+      int64_t ea[] = {cl, wl, d, cr}; int32_t ma[] = {lp, a, s, r};
+      int64_t eb[] = {wl, d, d, wr};  int32_t mb[] = {a, s, sp, b};
+      int64_t ec[] = {cl, cr, d, wr}; int32_t mc[] = {lp, r, sp, b};
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t0, 4, eb, mb, W, 4, ec, mc, t1, nullptr, nullptr, 0, st));
+    }
+    {  // Lnew[r,r',b] = T2 conj(A)[l',s',r']
+      int64_t ea[] = {cl, cr, d, wr}; int32_t ma[] = {lp, r, sp, b};
+      int64_t eb[] = {cl, d, cr};     int32_t mb[] = {lp, sp, rp};
+      int64_t ec[] = {cr, cr, wr};    int32_t mc[] = {r, rp, b};
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t1, 3, eb, mb, A, 3, ec, mc, Enew, nullptr, nullptr, TNB_CONJ_B, st));
+    }
+  } else {
+    // here E = R[r,r',c] with c = right MPO bond (wr), A[l,s,r], W[a,s,s',c]; labels b == c
+    {  // T1[r',c,l,s] = R[r,r',c] A[l,s,r]
+      int64_t ea[] = {cr, cr, wr}; int32_t ma[] = {r, rp, b};
+      int64_t eb[] = {cl, d, cr};  int32_t mb[] = {l, s, r};
+      int64_t ec[] = {cr, wr, cl, d}; int32_t mc[] = {rp, b, l, s};
+      TNB_TRY(contract_impl(h, dtype, 3, ea, ma, E, 3, eb, mb, A, 4, ec, mc, t0, nullptr, nullptr, 0, st));
+    }
+    {  // T2[r',l,a,s'] = T1 W[a,s,s',c]
+      int64_t ea[] = {cr, wr, cl, d}; int32_t ma[] = {rp, b, l, s};
+      int64_t eb[] = {wl, d, d, wr};  int32_t mb[] = {a, s, sp, b};
+      int64_t ec[] = {cr, cl, wl, d}; int32_t mc[] = {rp, l, a, sp};
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t0, 4, eb, mb, W, 4, ec, mc, t1, nullptr, nullptr, 0, st));
+    }
+    {  // Rnew[l,l',a] = T2 conj(A)[l',s',r']
+      int64_t ea[] = {cr, cl, wl, d}; int32_t ma[] = {rp, l, a, sp};
+      int64_t eb[] = {cl, d, cr};     int32_t mb[] = {lp, sp, rp};
+      int64_t ec[] = {cl, cl, wl};    int32_t mc[] = {l, lp, a};
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t1, 3, eb, mb, A, 3, ec, mc, Enew, nullptr, nullptr, TNB_CONJ_B, st));
+    }
+  }
+  return TNB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// device-resident Lanczos
+// ------------------------------------------------------------------------------------
+// Scalar pool layout (doubles, in h->scal): [16+j] alpha_j, [32+j] beta_j (residual norm after
+// step j), [48 + 2*i] complex overlap scratch, [64] lambda, [65] k_eff, [66] last-coefficient
+// residual |beta_k y_k|, [72+j] Ritz coefficients y_j, [90] nrm scratch.
+constexpr int S_ALPHA = 16, S_BETA = 32, S_OVL = 48, S_LAM = 64, S_KEFF = 65, S_RES = 66, S_Y = 72, S_NRM = 90;
+constexpr int KRYLOV_MAX = 12;
+
+// y <- y - c*x with c = scal[ci] (+ i*scal[ci+1] if complex)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) axmy_dev_kernel(double2* y, const double2* __restrict__ x, long long n2,
+                                                       const double* scal, int ci, int tail) {
+  const double cr = scal[ci], cim = CPLX ? scal[ci + 1] : 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    double2 a = x[i], b = y[i];
+    if (CPLX) { b.x -= cr * a.x - cim * a.y; b.y -= cr * a.y + cim * a.x; }
+    else { b.x -= cr * a.x; b.y -= cr * a.y; }
+    y[i] = b;
+  }
+  if (!CPLX && tail && blockIdx.x == 0 && threadIdx.x == 0) {
+    double* yt = (double*)(y + n2); const double* xt = (const double*)(x + n2);
+    yt[0] -= cr * xt[0];
+  }
+}
+
+// y <- x * (scal[ci] > tol ? 1/scal[ci] : 0)
+__global__ void __launch_bounds__(256) scale_inv_dev_kernel(double2* y, const double2* __restrict__ x, long long n2,
+                                                            const double* scal, int ci, double tol, int tail) {
+  const double b = scal[ci];
+  const double f = b > tol ? 1.0 / b : 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    double2 a = x[i];
+    a.x *= f; a.y *= f;
+    y[i] = a;
+  }
+  if (tail && blockIdx.x == 0 && threadIdx.x == 0) {
+    double* yt = (double*)(y + n2); const double* xt = (const double*)(x + n2);
+    yt[0] = xt[0] * f;
+  }
+}
+
+// out <- sum_j scal[S_Y+j] * V_j   (Ritz vector), V_j = V + j*stride2 (in double2 units)
+__global__ void __launch_bounds__(256) ritz_combine_kernel(double2* out, const double2* __restrict__ V,
+                                                           long long stride2, long long n2, int k,
+                                                           const double* scal, int tail) {
+  double y[KRYLOV_MAX];
+  for (int j = 0; j < k; ++j) y[j] = scal[S_Y + j];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int j = 0; j < k; ++j) { const double2 v = V[j * stride2 + i]; acc.x += y[j] * v.x; acc.y += y[j] * v.y; }
+    out[i] = acc;
+  }
+  if (tail && blockIdx.x == 0 && threadIdx.x == 0) {
+    double acc = 0;
+    for (int j = 0; j < k; ++j) acc += y[j] * ((const double*)(V + j * stride2 + n2))[0];
+    ((double*)(out + n2))[0] = acc;
+  }
+}
+
+// Lowest eigenpair of the k x k symmetric tridiagonal (alpha, beta) by cyclic Jacobi -- one
+// thread; k <= 12.  k_eff = number of Krylov vectors actually spanned (first beta <= tol cuts).
+__global__ void ritz_kernel(double* scal, int k, double tol) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int ke = k;
+  for (int j = 0; j < k - 1; ++j) if (!(scal[S_BETA + j] > tol)) { ke = j + 1; break; }
+  double T[KRYLOV_MAX][KRYLOV_MAX], U[KRYLOV_MAX][KRYLOV_MAX];
+  for (int i = 0; i < ke; ++i) for (int j = 0; j < ke; ++j) { T[i][j] = 0.0; U[i][j] = i == j ? 1.0 : 0.0; }
+  for (int i = 0; i < ke; ++i) T[i][i] = scal[S_ALPHA + i];
+  for (int i = 0; i < ke - 1; ++i) T[i][i + 1] = T[i + 1][i] = scal[S_BETA + i];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < ke; ++i) for (int j = i + 1; j < ke; ++j) off += T[i][j] * T[i][j];
+    if (off < 1e-300) break;
+    for (int p = 0; p < ke; ++p) for (int q = p + 1; q < ke; ++q) {
+      const double apq = T[p][q];
+      if (apq == 0.0) continue;
+      const double tau = (T[q][q] - T[p][p]) / (2.0 * apq);
+      const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+      const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+      for (int i = 0; i < ke; ++i) { const double a = T[i][p], b = T[i][q]; T[i][p] = c * a - s * b; T[i][q] = s * a + c * b; }
+      for (int i = 0; i < ke; ++i) { const double a = T[p][i], b = T[q][i]; T[p][i] = c * a - s * b; T[q][i] = s * a + c * b; }
+      for (int i = 0; i < ke; ++i) { const double a = U[i][p], b = U[i][q]; U[i][p] = c * a - s * b; U[i][q] = s * a + c * b; }
+    }
+  }
+  int best = 0;
+  for (int i = 1; i < ke; ++i) if (T[i][i] < T[best][best]) best = i;
+  double nrm = 0;
+  for (int i = 0; i < ke; ++i) nrm += U[i][best] * U[i][best];
+  nrm = sqrt(nrm);
+  for (int i = 0; i < k; ++i) scal[S_Y + i] = i < ke ? U[i][best] / nrm : 0.0;
+  scal[S_LAM] = T[best][best];
+  scal[S_KEFF] = (double)ke;
+  scal[S_RES] = fabs(scal[S_BETA + ke - 1] * U[ke - 1][best] / nrm);
+}
+
+static int vec_grid(Handle* h, long long n2) {
+  return (int)std::max<long long>(1, std::min<long long>((n2 + 1023) / 1024, (long long)h->num_sms * 8));
+}
+
+int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                 const void* W2, const void* R, void* phi, int krylovdim, int maxiter, double tol,
+                 double* energy, int* n_matvec, cudaStream_t st) {
+  TNB_TRY(check_dims(h, d));
+  if (krylovdim < 1 || krylovdim > KRYLOV_MAX) return set_err(h, TNB_ERR_BAD_ARG, "lanczos: krylovdim must be in 1..%d", KRYLOV_MAX);
+  if (maxiter < 1) return set_err(h, TNB_ERR_BAD_ARG, "lanczos: maxiter < 1");
+  const bool cplx = dtype == TNB_C128;
+  const size_t es = elsize(dtype);
+  const long long n = (long long)d->chiL * d->chiR * d->d1 * d->d2;
+  const long long nd = cplx ? 2 * n : n;      // length in doubles
+  const long long n2 = nd / 2;
+  const int tail = (int)(nd & 1);
+  const size_t vbytes = al256((size_t)n * es);
+  ws_reset(h);
+  const size_t hw = heff_ws_bytes(dtype, d);
+  TNB_TRY(ws_require(h, hw + (size_t)(krylovdim + 1) * vbytes + 1024));
+  void *t0, *t1, *Vb, *w;
+  TNB_TRY(ws_alloc(h, hw / 2, &t0));
+  TNB_TRY(ws_alloc(h, hw / 2, &t1));
+  TNB_TRY(ws_alloc(h, (size_t)krylovdim * vbytes, &Vb));
+  TNB_TRY(ws_alloc(h, vbytes, &w));
+  const long long stride2 = (long long)(vbytes / 16);
+  auto V = [&](int j) { return (void*)((char*)Vb + (size_t)j * vbytes); };
+  const int grid = vec_grid(h, n2);
+  double* scal = h->scal;
+  int nmv = 0;
+  for (int it = 0; it < maxiter; ++it) {
+    // v1 = phi / ||phi||
+    TNB_TRY(nrm2_impl(h, dtype, n, phi, scal + S_NRM, st));
+    scale_inv_dev_kernel<<<grid, 256, 0, st>>>((double2*)V(0), (const double2*)phi, n2, scal, S_NRM, 0.0, tail);
+    h->launches++;
+    for (int j = 0; j < krylovdim; ++j) {
+      TNB_TRY(heff_core(h, dtype, d, L, W1, W2, R, V(j), w, t0, t1, st));
+      ++nmv;
+      // alpha_j = Re <v_j, w>
+      TNB_TRY(dot_impl(h, dtype, n, V(j), w, scal + S_OVL, st));
+      TNB_CUDA(h, cudaMemcpyAsync(scal + S_ALPHA + j, scal + S_OVL, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      // w -= <v_i, w> v_i for all i <= j (modified Gram-Schmidt; covers the alpha_j v_j and
+      // beta_{j-1} v_{j-1} terms of the three-term recurrence, then a second pass = full reorth.)
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int i = j; i >= 0; --i) {
+          if (!(pass == 0 && i == j)) TNB_TRY(dot_impl(h, dtype, n, V(i), w, scal + S_OVL, st));
+          if (cplx) axmy_dev_kernel<true><<<grid, 256, 0, st>>>((double2*)w, (const double2*)V(i), n2, scal, S_OVL, 0);
+          else axmy_dev_kernel<false><<<grid, 256, 0, st>>>((double2*)w, (const double2*)V(i), n2, scal, S_OVL, tail);
+          h->launches++;
+        }
+      }
+      TNB_TRY(nrm2_impl(h, dtype, n, w, scal + S_BETA + j, st));
+      if (j + 1 < krylovdim) {
+        scale_inv_dev_kernel<<<grid, 256, 0, st>>>((double2*)V(j + 1), (const double2*)w, n2, scal, S_BETA + j, tol, tail);
+        h->launches++;
+      }
+    }
+    ritz_kernel<<<1, 32, 0, st>>>(scal, krylovdim, tol);
+    ritz_combine_kernel<<<grid, 256, 0, st>>>((double2*)phi, (const double2*)Vb, stride2, n2, krylovdim, scal, tail);
+    h->launches += 2;
+    TNB_CUDA(h, cudaGetLastError());
+    if (it + 1 < maxiter) {
+      TNB_CUDA(h, cudaMemcpyAsync(h->scal_host + S_LAM, scal + S_LAM, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      TNB_CUDA(h, cudaStreamSynchronize(st));
+      if (h->scal_host[S_RES] < tol) break;
+    }
+  }
+  // normalise (y is unit and V orthonormal, so this only removes rounding drift)
+  TNB_TRY(nrm2_impl(h, dtype, n, phi, scal + S_NRM, st));
+  scale_inv_dev_kernel<<<grid, 256, 0, st>>>((double2*)phi, (const double2*)phi, n2, scal, S_NRM, 0.0, tail);
+  h->launches++;
+  TNB_CUDA(h, cudaMemcpyAsync(h->scal_host + S_LAM, scal + S_LAM, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(h, cudaStreamSynchronize(st));
+  if (energy) *energy = h->scal_host[S_LAM];
+  if (n_matvec) *n_matvec = nmv;
+  return TNB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// noise term
+// ------------------------------------------------------------------------------------
+int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                    const void* W2, const void* R, const void* phi, int ortho, double noise,
+                    int accumulate, void* rho, void* t0, void* t1, cudaStream_t st) {
+  const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
+  double alpha[2] = {noise, 0.0}, beta[2] = {accumulate ? 1.0 : 0.0, 0.0};
+  if (ortho == TNB_ORTHO_LEFT) {
+    {  // T1[s1,s2,r,l',a] = phi L          (re-ordered: (phi*L)*W1 instead of (L*W1)*phi)
+      int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
+      int64_t eb[] = {cl, cl, wl};     int32_t mb[] = {mL, mLp, mA};
+      int64_t ec[] = {d1, d2, cr, cl, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+    }
+    {  // nt[s2,r,l',s1',b] = T1 W1
+      int64_t ea[] = {d1, d2, cr, cl, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
+      int64_t eb[] = {wl, d1, d1, wm};     int32_t mb[] = {mA, mS1, mS1p, mB};
+      int64_t ec[] = {d2, cr, cl, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W1, 5, ec, mc, t1, nullptr, nullptr, 0, st));
+    }
+    {  // rho[l',s1',l'',s1''] (+)= noise * nt conj(nt)
+      int64_t ea[] = {d2, cr, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
+      int32_t mb[] = {mS2, mR, mLpp, mS1pp, mB};
+      int64_t ec[] = {cl, d1, cl, d1};     int32_t mc[] = {mLp, mS1p, mLpp, mS1pp};
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B, st));
+    }
+  } else {
+    {  // T1[l,s1,s2,r',c] = phi R
+      int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
+      int64_t eb[] = {cr, cr, wr};     int32_t mb[] = {mR, mRp, mC};
+      int64_t ec[] = {cl, d1, d2, cr, wr}; int32_t mc[] = {mL, mS1, mS2, mRp, mC};
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, R, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+    }
+    {  // nt[l,s1,r',b,s2'] = T1 W2[b,s2,s2',c]
+      int64_t ea[] = {cl, d1, d2, cr, wr}; int32_t ma[] = {mL, mS1, mS2, mRp, mC};
+      int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
+      int64_t ec[] = {cl, d1, cr, wm, d2}; int32_t mc[] = {mL, mS1, mRp, mB, mS2p};
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W2, 5, ec, mc, t1, nullptr, nullptr, 0, st));
+    }
+    {  // rho[s2',r',s2'',r''] (+)= noise * nt conj(nt)
+      int64_t ea[] = {cl, d1, cr, wm, d2}; int32_t ma[] = {mL, mS1, mRp, mB, mS2p};
+      int32_t mb[] = {mL, mS1, mRpp, mB, mS2pp};
+      int64_t ec[] = {d2, cr, d2, cr};     int32_t mc[] = {mS2p, mRp, mS2pp, mRpp};
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B, st));
+    }
+  }
+  return TNB_OK;
+}
+
+size_t heff_workspace_bytes(int dtype, const tnb_bond_dims* d) { return heff_ws_bytes(dtype, d); }
+int heff_core_pub(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1, const void* W2,
+                  const void* R, const void* phi, void* out, void* t0, void* t1, cudaStream_t st) {
+  return heff_core(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+#define H ((Handle*)h)
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+int tnb_heff_apply(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,
+                   const void* W2, const void* R, const void* phi, void* out, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L || !W1 || !W2 || !R || !phi || !out) return set_err(H, TNB_ERR_BAD_ARG, "heff_apply: null pointer");
+  return heff_apply_impl(H, dtype, dims, L, W1, W2, R, phi, out, ST);
+}
+
+int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,
+                        const void* W2, const void* R, const void* phi_host, void* out_host, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L || !W1 || !W2 || !R || !phi_host || !out_host) return set_err(H, TNB_ERR_BAD_ARG, "heff_apply_host: null pointer");
+  TNB_TRY(check_dims(H, dims));
+  const size_t nb = (size_t)dims->chiL * dims->chiR * dims->d1 * dims->d2 * elsize(dtype);
+  ws_reset(H);
+  const size_t hw = heff_workspace_bytes(dtype, dims);
+  TNB_TRY(ws_require(H, hw + 2 * al256(nb)));
+  void *t0, *t1, *dphi, *dout;
+  TNB_TRY(ws_alloc(H, hw / 2, &t0));
+  TNB_TRY(ws_alloc(H, hw / 2, &t1));
+  TNB_TRY(ws_alloc(H, nb, &dphi));
+  TNB_TRY(ws_alloc(H, nb, &dout));
+  TNB_CUDA(H, cudaMemcpyAsync(dphi, phi_host, nb, cudaMemcpyHostToDevice, ST));
+  TNB_TRY(heff_core_pub(H, dtype, dims, L, W1, W2, R, dphi, dout, t0, t1, ST));
+  TNB_CUDA(H, cudaMemcpyAsync(out_host, dout, nb, cudaMemcpyDeviceToHost, ST));
+  TNB_CUDA(H, cudaStreamSynchronize(ST));
+  return TNB_OK;
+}
+
+int tnb_env_update_left(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d, int32_t wL,
+                        int32_t wR, const void* L, const void* A, const void* W, void* Lnew, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L || !A || !W || !Lnew) return set_err(H, TNB_ERR_BAD_ARG, "env_update_left: null pointer");
+  return env_update_impl(H, dtype, true, chiL, chiR, d, wL, wR, L, A, W, Lnew, ST);
+}
+
+int tnb_env_update_right(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d, int32_t wL,
+                         int32_t wR, const void* R, const void* A, const void* W, void* Rnew, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!R || !A || !W || !Rnew) return set_err(H, TNB_ERR_BAD_ARG, "env_update_right: null pointer");
+  return env_update_impl(H, dtype, false, chiL, chiR, d, wL, wR, R, A, W, Rnew, ST);
+}
+
+int tnb_eigsolve_lanczos(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,
+                         const void* W2, const void* R, void* phi, int krylovdim, int maxiter, double tol,
+                         double* energy, int* n_matvec, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L || !W1 || !W2 || !R || !phi) return set_err(H, TNB_ERR_BAD_ARG, "eigsolve_lanczos: null pointer");
+  return lanczos_impl(H, dtype, dims, L, W1, W2, R, phi, krylovdim, maxiter, tol, energy, n_matvec, ST);
+}
+
+int tnb_noise_term(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,
+                   const void* W2, const void* R, const void* phi, int ortho, double noise, int accumulate,
+                   void* rho, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L || !W1 || !W2 || !R || !phi || !rho) return set_err(H, TNB_ERR_BAD_ARG, "noise_term: null pointer");
+  TNB_TRY(check_dims(H, dims));
+  ws_reset(H);
+  const size_t hw = heff_workspace_bytes(dtype, dims);
+  TNB_TRY(ws_require(H, hw));
+  void *t0, *t1;
+  TNB_TRY(ws_alloc(H, hw / 2, &t0));
+  TNB_TRY(ws_alloc(H, hw / 2, &t1));
+  return noise_term_impl(H, dtype, dims, L, W1, W2, R, phi, ortho, noise, accumulate, rho, t0, t1, ST);
+}
+
+}  // extern "C"

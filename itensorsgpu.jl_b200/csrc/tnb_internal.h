@@ -1,0 +1,115 @@
+// Internal declarations shared by the translation units of libtnb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tnb200.h"
+
+namespace tnb {
+
+constexpr int MAXG = 12;  // modes per group (M / N / K) after merging
+
+// One mode group of a contraction, linearised in mixed radix (ext[0] fastest).
+// sX / sY are the element strides of each mode in the two tensors that carry the group:
+//   M group: X = A, Y = C      N group: X = B, Y = C      K group: X = A, Y = B
+struct Group {
+  int n;
+  int ext[MAXG];
+  long long sX[MAXG];
+  long long sY[MAXG];
+};
+
+struct GemmParams {
+  Group gm, gn, gk;
+  int M, N, K;
+  const void* A;
+  const void* B;
+  void* C;
+  double alpha_re, alpha_im, beta_re, beta_im;
+  int conjA, conjB;
+  int tilesM, tilesN, groupM;
+};
+
+struct Handle {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  char* ws = nullptr;       // workspace arena
+  size_t ws_bytes = 0;
+  size_t ws_off = 0;        // bump pointer (reset by each public entry point)
+  double* scal = nullptr;   // small device scalar pool (256 doubles)
+  double* scal_host = nullptr;  // pinned mirror
+  uint64_t launches = 0;
+  cudaStream_t copy_stream = nullptr;
+  double* partials = nullptr;   // per-block partial sums for reductions (8192 doubles)
+  unsigned* counter = nullptr;  // last-block-done ticket (self-resetting)
+};
+constexpr int RED_MAX_BLOCKS = 1024;
+
+int set_err(Handle* h, int code, const char* fmt, ...);
+int check_cuda(Handle* h, cudaError_t e, const char* what);
+// Bump-allocate from the arena (256-byte aligned).  Grows the arena if needed (device sync).
+int ws_alloc(Handle* h, size_t bytes, void** out);
+// Ensure the arena holds at least `bytes` BEFORE a sequence of ws_alloc calls, so that
+// pointers handed out earlier in the same entry point stay valid.
+int ws_require(Handle* h, size_t bytes);
+inline void ws_reset(Handle* h) { h->ws_off = 0; }
+
+#define TNB_CUDA(h, call)                                   \
+  do {                                                      \
+    int _s = tnb::check_cuda((h), (call), #call);           \
+    if (_s) return _s;                                      \
+  } while (0)
+#define TNB_TRY(call)        \
+  do {                       \
+    int _s = (call);         \
+    if (_s) return _s;       \
+  } while (0)
+
+// ---- contraction (contract.cu)
+int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
+                  const void* A, int nB, const int64_t* extB, const int32_t* modeB,
+                  const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                  const void* alpha, const void* beta, int flags, cudaStream_t st);
+// plain column-major GEMM helper built on the same kernel:
+//   C[m x n] (ldc) <- alpha * op(A) * op(B) + beta * C ; op = N / T / C(onj-transpose)
+int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
+              const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
+              const void* beta, void* C, int64_t ldc, cudaStream_t st);
+
+// ---- vector ops (vecops.cu)
+int permute_axpby_impl(Handle* h, int dtype, int n, const int64_t* extA, const int32_t* modeA,
+                       const void* A, const int32_t* modeB, void* B, const void* alpha,
+                       const void* beta, cudaStream_t st);
+int scale_impl(Handle* h, int dtype, int64_t n, void* x, const void* alpha, cudaStream_t st);
+int dot_impl(Handle* h, int dtype, int64_t n, const void* x, const void* y, void* result_dev,
+             cudaStream_t st);
+int nrm2_impl(Handle* h, int dtype, int64_t n, const void* x, double* result_dev,
+              cudaStream_t st);
+int truncate_impl(Handle* h, const double* P_dev, int64_t len, int64_t maxdim, int64_t mindim,
+                  double cutoff, int flags, int64_t* n_keep, double* truncerr, double* docut,
+                  cudaStream_t st);
+
+// ---- fused DMRG pieces (heff.cu)
+size_t heff_workspace_bytes(int dtype, const tnb_bond_dims* d);
+int heff_core_pub(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                  const void* W2, const void* R, const void* phi, void* out, void* t0, void* t1,
+                  cudaStream_t st);
+int heff_apply_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                    const void* W2, const void* R, const void* phi, void* out, cudaStream_t st);
+int env_update_impl(Handle* h, int dtype, bool left, int64_t cl, int64_t cr, int32_t d, int32_t wl,
+                    int32_t wr, const void* E, const void* A, const void* W, void* Enew,
+                    cudaStream_t st);
+int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                 const void* W2, const void* R, void* phi, int krylovdim, int maxiter, double tol,
+                 double* energy, int* n_matvec, cudaStream_t st);
+int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                    const void* W2, const void* R, const void* phi, int ortho, double noise,
+                    int accumulate, void* rho, void* t0, void* t1, cudaStream_t st);
+
+inline size_t elsize(int dtype) { return dtype == TNB_C128 ? 16 : 8; }
+
+}  // namespace tnb
