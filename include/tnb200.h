@@ -160,6 +160,14 @@ typedef struct {
 int tnb_heff_apply(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
                    const void* W1, const void* W2, const void* R, const void* phi,
                    void* out, void* stream);
+/* Multi-GPU form: the OUTPUT bond l' is sharded.  This rank holds the slab
+ * L_slab[l, l'_shard, a] (lp_extent columns of l'), full phi, W1, W2, R, and produces
+ * out_slab[l'_shard, s1', s2', r'] -- 1/G of every contraction, no reduction; the caller
+ * all-gathers the slabs (NCCL) when the next matvec needs the full vector.  (The reference's
+ * only multi-GPU attempt is dead cuBLASMg code: src/tensor/dense.jl:195-265.) */
+int tnb_heff_apply_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int64_t lp_extent,
+                         const void* L_slab, const void* W1, const void* W2, const void* R,
+                         const void* phi, void* out_slab, void* stream);
 /* Same, phi and out in HOST memory (pinned or pageable): H2D + apply + D2H, synchronous.
  * This is the end-to-end form timed by bench.py `e2e`. */
 int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,

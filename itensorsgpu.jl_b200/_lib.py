@@ -59,6 +59,7 @@ SIGNATURES = {
     "tnb_eigh_trunc": (_int, [_vp, _int, _i64, _vp, _i64, _i64, _dbl, _int, _int, _vp, _vp, _pi64, _pdbl, _vp]),
     "tnb_qr": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "tnb_heff_apply": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_heff_apply_shard": (_int, [_vp, _int, _pbd, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnb_heff_apply_host": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnb_env_update_left": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tnb_env_update_right": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -27,32 +27,34 @@ static size_t heff_ws_bytes(int dtype, const tnb_bond_dims* d) {
 }
 
 // out <- (((phi*L)*W1)*W2)*R using two ping-pong temporaries t0,t1 (each base*max(w) elements)
-static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+// `clp` = extent of the output bond l' held by this call: chiL normally, chiL/G when the
+// output bond is sharded over G GPUs (L is then the slab L[:, l'_shard, :]).
+static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* L, const void* W1,
                      const void* W2, const void* R, const void* phi, void* out, void* t0, void* t1,
                      cudaStream_t st) {
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
   {  // 1. T1[s1,s2,r,l',a] = phi[l,s1,s2,r] L[l,l',a]
     int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
-    int64_t eb[] = {cl, cl, wl};     int32_t mb[] = {mL, mLp, mA};
-    int64_t ec[] = {d1, d2, cr, cl, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
+    int64_t eb[] = {cl, clp, wl};    int32_t mb[] = {mL, mLp, mA};
+    int64_t ec[] = {d1, d2, cr, clp, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
     TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
   }
   {  // 2. T2[s2,r,l',s1',b] = T1 W1[a,s1,s1',b]
-    int64_t ea[] = {d1, d2, cr, cl, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
-    int64_t eb[] = {wl, d1, d1, wm};     int32_t mb[] = {mA, mS1, mS1p, mB};
-    int64_t ec[] = {d2, cr, cl, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
+    int64_t ea[] = {d1, d2, cr, clp, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
+    int64_t eb[] = {wl, d1, d1, wm};      int32_t mb[] = {mA, mS1, mS1p, mB};
+    int64_t ec[] = {d2, cr, clp, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
     TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W1, 5, ec, mc, t1, nullptr, nullptr, 0, st));
   }
   {  // 3. T3[r,l',s1',s2',c] = T2 W2[b,s2,s2',c]
-    int64_t ea[] = {d2, cr, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
-    int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
-    int64_t ec[] = {cr, cl, d1, d2, wr}; int32_t mc[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t ea[] = {d2, cr, clp, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
+    int64_t eb[] = {wm, d2, d2, wr};      int32_t mb[] = {mB, mS2, mS2p, mC};
+    int64_t ec[] = {cr, clp, d1, d2, wr}; int32_t mc[] = {mR, mLp, mS1p, mS2p, mC};
     TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 4, eb, mb, W2, 5, ec, mc, t0, nullptr, nullptr, 0, st));
   }
   {  // 4. out[l',s1',s2',r'] = T3 R[r,r',c]
-    int64_t ea[] = {cr, cl, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
-    int64_t eb[] = {cr, cr, wr};         int32_t mb[] = {mR, mRp, mC};
-    int64_t ec[] = {cl, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
+    int64_t ea[] = {cr, clp, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t eb[] = {cr, cr, wr};          int32_t mb[] = {mR, mRp, mC};
+    int64_t ec[] = {clp, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
     TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 3, eb, mb, R, 4, ec, mc, out, nullptr, nullptr, 0, st));
   }
   return TNB_OK;
@@ -74,7 +76,25 @@ int heff_apply_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
   void *t0, *t1;
   TNB_TRY(ws_alloc(h, need / 2, &t0));
   TNB_TRY(ws_alloc(h, need / 2, &t1));
-  return heff_core(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
+  return heff_core(h, dtype, d, d->chiL, L, W1, W2, R, phi, out, t0, t1, st);
+}
+
+int heff_apply_shard_impl(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* Lslab,
+                          const void* W1, const void* W2, const void* R, const void* phi, void* out,
+                          cudaStream_t st) {
+  TNB_TRY(check_dims(h, d));
+  if (clp < 1 || clp > d->chiL) return set_err(h, TNB_ERR_BAD_ARG, "heff_apply_shard: bad shard extent");
+  ws_reset(h);
+  tnb_bond_dims ds = *d;  // workspace scales with the shard
+  const size_t base = (size_t)clp * d->chiR * d->d1 * d->d2;
+  const size_t w = std::max({d->wL, d->wM, d->wR});
+  const size_t half = al256(base * w * elsize(dtype));
+  (void)ds;
+  TNB_TRY(ws_require(h, 2 * half));
+  void *t0, *t1;
+  TNB_TRY(ws_alloc(h, half, &t0));
+  TNB_TRY(ws_alloc(h, half, &t1));
+  return heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, out, t0, t1, st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -271,7 +291,7 @@ int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, co
     scale_inv_dev_kernel<<<grid, 256, 0, st>>>((double2*)V(0), (const double2*)phi, n2, scal, S_NRM, 0.0, tail);
     h->launches++;
     for (int j = 0; j < krylovdim; ++j) {
-      TNB_TRY(heff_core(h, dtype, d, L, W1, W2, R, V(j), w, t0, t1, st));
+      TNB_TRY(heff_core(h, dtype, d, d->chiL, L, W1, W2, R, V(j), w, t0, t1, st));
       ++nmv;
       // alpha_j = Re <v_j, w>
       TNB_TRY(dot_impl(h, dtype, n, V(j), w, scal + S_OVL, st));
@@ -366,7 +386,7 @@ int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
 size_t heff_workspace_bytes(int dtype, const tnb_bond_dims* d) { return heff_ws_bytes(dtype, d); }
 int heff_core_pub(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1, const void* W2,
                   const void* R, const void* phi, void* out, void* t0, void* t1, cudaStream_t st) {
-  return heff_core(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
+  return heff_core(h, dtype, d, d->chiL, L, W1, W2, R, phi, out, t0, t1, st);
 }
 
 }  // namespace tnb
@@ -382,6 +402,14 @@ int tnb_heff_apply(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const v
   if (!h) return TNB_ERR_BAD_ARG;
   if (!L || !W1 || !W2 || !R || !phi || !out) return set_err(H, TNB_ERR_BAD_ARG, "heff_apply: null pointer");
   return heff_apply_impl(H, dtype, dims, L, W1, W2, R, phi, out, ST);
+}
+
+int tnb_heff_apply_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int64_t lp_extent,
+                         const void* L_slab, const void* W1, const void* W2, const void* R, const void* phi,
+                         void* out_slab, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L_slab || !W1 || !W2 || !R || !phi || !out_slab) return set_err(H, TNB_ERR_BAD_ARG, "heff_apply_shard: null pointer");
+  return heff_apply_shard_impl(H, dtype, dims, lp_extent, L_slab, W1, W2, R, phi, out_slab, ST);
 }
 
 int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,

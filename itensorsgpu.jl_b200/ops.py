@@ -236,6 +236,21 @@ def heff_apply(L, W1, W2, R, phi, out=None):
     return out
 
 
+def heff_apply_shard(Lslab, W1, W2, R, phi, out=None):
+    """Output-bond-sharded H_eff*phi: Lslab[l, l'_shard, a] -> out[l'_shard, s1', s2', r']."""
+    h = _lib.handle()
+    cl, d1, d2, cr = phi.dims
+    clp = Lslab.dims[1]
+    if Lslab.dims[0] != cl or R.dims[:2] != (cr, cr):
+        raise _lib.DimensionMismatch(2, "environment / phi bond dims differ")
+    bd = BondDims(cl, cr, d1, d2, W1.dims[0], W1.dims[3], W2.dims[3])
+    if out is None:
+        out = DTensor.empty((clp, d1, d2, cr), phi.dtype, phi.data.device)
+    h.check(h.lib.tnb_heff_apply_shard(h.h, _dt(phi.data), C.byref(bd), clp, _ptr(Lslab.data), _ptr(W1.data),
+                                       _ptr(W2.data), _ptr(R.data), _ptr(phi.data), _ptr(out.data), _stream()))
+    return out
+
+
 def heff_apply_host(L, W1, W2, R, phi_host, out_host, dims):
     """phi_host/out_host: pinned CPU torch tensors (flat); L.. on device.  Synchronous."""
     h = _lib.handle()

@@ -123,8 +123,7 @@ def test_linearity_at_large_size():
     err = (torch.linalg.vector_norm(C3.data - ref) / torch.linalg.vector_norm(ref)).item()
     assert err < 1e-12
     # and against cuBLAS on the same box (library check, not the oracle)
-    refm = (A1.data.view(chi, 4 * chi).double() @ B.data.view(5 * chi, chi).t())  # row-major views of the F buffers
-    # A1 flat F-order (l,s,t,r): as row-major [r*t*s, l]; B flat (l,p,a): row-major [a*p, l]
+    # A1 flat F-order (l,s,t,r) = row-major [(r,t,s), l]; B flat (l,p,a) = row-major [(a,p), l]
     got = C1.data.view(5 * chi, 4 * chi)  # F-order (s,t,r,p,a) -> row-major [(a,p), (r,t,s)]
     want = B.data.view(5 * chi, chi) @ A1.data.view(4 * chi, chi).t()
     err2 = (torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want)).item()
