@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 
 namespace tnb {
@@ -63,9 +64,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_>
+template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_, int MINB_>
 struct Cfg {
-  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int NT = WARPS_M * WARPS_N * 32;
   static constexpr int MI = WM / 8, NI = WN / 8;
@@ -85,8 +86,13 @@ struct TileGeom {
   static constexpr int ELEMS = ELEMS_K > ELEMS_R ? ELEMS_K : ELEMS_R;
 };
 
-// Issue the cp.async copies of one operand tile.  `rowoff` are this thread's precomputed
-// free-index offsets (CONTIG_K: one per pass; CONTIG_R: one in total), `rowok` their masks.
+// cp.async staging of one operand tile.  Per thread: `rowoff[]` = element offsets of the tile
+// rows it copies (registers, decoded once per CTA; -1 = out of range).  Per K tile `begin()`
+// decodes the K offset(s) with integer ALU work only; `issue(pass)` is then one select, one
+// 64-bit add and one LDGSTS.  The kernel issues the passes inside the LAST k-step of the tile
+// being computed: LDGSTS share the MIO queue with the fragment LDS, and a copy burst placed
+// before the tile's fragment loads delays them and starves the DMMA pipe (measured: 30.9 vs
+// 34+ TFLOP/s).
 template <bool CPLX, bool CONTIG_K, int VEC, int ROWS, int BK, int NT, bool KY>
 struct Loader {
   using G = TileGeom<CPLX, ROWS, BK>;
@@ -97,55 +103,54 @@ struct Loader {
   static constexpr int KPP = NT / VPK;                       //           k-rows per pass
   static constexpr int NPASS = CONTIG_K ? (ROWS / RPP) : (BK / KPP);
   static constexpr int NROW = CONTIG_K ? NPASS : 1;
+  static constexpr int NKO = CONTIG_K ? 1 : NPASS;
   static_assert(NT % (CONTIG_K ? VPR : VPK) == 0, "thread mapping");
   static_assert(NPASS >= 1, "tile too small for the CTA");
 
   long long rowoff[NROW];
-  bool rowok[NROW];
+  long long koff[NKO];   // -1 = k out of range
 
   __device__ __forceinline__ void init(const Group& g, int row0, int R, int tid) {
     if (CONTIG_K) {
 #pragma unroll
       for (int i = 0; i < NPASS; ++i) {
-        int r = row0 + tid / VPR + i * RPP;
-        rowok[i] = r < R;
-        rowoff[i] = rowok[i] ? decode<false>(g, r) : 0;
+        const int r = row0 + tid / VPR + i * RPP;
+        rowoff[i] = (r < R) ? decode<false>(g, r) : -1;
       }
     } else {
-      int r = row0 + (tid % VPK) * VEC;
-      rowok[0] = r < R;
-      rowoff[0] = rowok[0] ? decode<false>(g, r) : 0;
+      const int r = row0 + (tid % VPK) * VEC;
+      rowoff[0] = (r < R) ? decode<false>(g, r) : -1;
     }
   }
 
-  __device__ __forceinline__ void issue(const char* base, char* smem, const Group& gk, int k0,
-                                        int K, int tid) const {
+  __device__ __forceinline__ void begin(const Group& gk, int k0, int K, int tid) {
+    if (CONTIG_K) {
+      const int k = k0 + (tid % VPR) * VEC;
+      koff[0] = (k < K) ? decode<KY>(gk, k) : -1;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        const int k = k0 + tid / VPK + i * KPP;
+        koff[i] = (k < K) ? decode<KY>(gk, k) : -1;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void issue(int pass, const char* base, char* smem, int tid) const {
     if (CONTIG_K) {
       const int kv = (tid % VPR) * VEC;
-      const int k = k0 + kv;
-      const bool kok = k < K;
-      const long long koff = kok ? decode<KY>(gk, k) : 0;
-      const int r = tid / VPR;
-#pragma unroll
-      for (int i = 0; i < NPASS; ++i) {
-        char* dst = smem + (size_t)((r + i * RPP) * G::PK + kv) * EB;
-        const bool ok = kok && rowok[i];
-        const char* src = base + (ok ? (rowoff[i] + koff) * EB : 0);
-        if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
-      }
+      const int r = tid / VPR + pass * RPP;
+      char* dst = smem + (size_t)(r * G::PK + kv) * EB;
+      const bool ok = (koff[0] >= 0) && (rowoff[pass] >= 0);
+      const char* src = base + (ok ? (rowoff[pass] + koff[0]) * EB : 0);
+      if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
     } else {
       const int rv = (tid % VPK) * VEC;
-      const int kb = tid / VPK;
-#pragma unroll
-      for (int i = 0; i < NPASS; ++i) {
-        const int kl = kb + i * KPP;
-        const int k = k0 + kl;
-        const bool ok = rowok[0] && (k < K);
-        const long long koff = ok ? decode<KY>(gk, k) : 0;
-        char* dst = smem + (size_t)(kl * G::PR + rv) * EB;
-        const char* src = base + (ok ? (rowoff[0] + koff) * EB : 0);
-        if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
-      }
+      const int kl = tid / VPK + pass * KPP;
+      char* dst = smem + (size_t)(kl * G::PR + rv) * EB;
+      const bool ok = (rowoff[0] >= 0) && (koff[pass] >= 0);
+      const char* src = base + (ok ? (rowoff[0] + koff[pass]) * EB : 0);
+      if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
     }
   }
 };
@@ -153,8 +158,8 @@ struct Loader {
 // ------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------
-template <bool CPLX, bool AK, bool BKM, int VA, int VB, class CFG>
-__global__ void __launch_bounds__(CFG::NT, 1) contract_kernel(const __grid_constant__ GemmParams p) {
+template <bool CPLX, bool AK, bool BKM, int VA, int VB, class CFG, int DBG = 0>
+__global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __grid_constant__ GemmParams p) {
   constexpr int BM = CFG::BM, BN = CFG::BN, BK = CFG::BK, NT = CFG::NT, ST = CFG::STAGES;
   constexpr int MI = CFG::MI, NI = CFG::NI;
   constexpr int EB = CPLX ? 16 : 8;
@@ -184,8 +189,10 @@ __global__ void __launch_bounds__(CFG::NT, 1) contract_kernel(const __grid_const
   }
   const int m0 = tm * BM, n0 = tn * BN;
 
-  Loader<CPLX, AK, VA, BM, BK, NT, false> la;
-  Loader<CPLX, BKM, VB, BN, BK, NT, true> lb;
+  using LA = Loader<CPLX, AK, VA, BM, BK, NT, false>;
+  using LB = Loader<CPLX, BKM, VB, BN, BK, NT, true>;
+  LA la;
+  LB lb;
   la.init(p.gm, m0, p.M, tid);
   lb.init(p.gn, n0, p.N, tid);
 
@@ -205,82 +212,119 @@ __global__ void __launch_bounds__(CFG::NT, 1) contract_kernel(const __grid_const
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) {
     if (s < KT) {
-      la.issue(Ab, (char*)smem + s * STAGE_BYTES, p.gk, s * BK, p.K, tid);
-      lb.issue(Bb, (char*)smem + s * STAGE_BYTES + A_BYTES, p.gk, s * BK, p.K, tid);
+      la.begin(p.gk, s * BK, p.K, tid);
+      lb.begin(p.gk, s * BK, p.K, tid);
+#pragma unroll
+      for (int c = 0; c < LA::NPASS; ++c) la.issue(c, Ab, (char*)smem + s * STAGE_BYTES, tid);
+#pragma unroll
+      for (int c = 0; c < LB::NPASS; ++c) lb.issue(c, Bb, (char*)smem + s * STAGE_BYTES + A_BYTES, tid);
     }
     cp_async_commit();
   }
 
   const double sa = p.conjA ? -1.0 : 1.0, sb = p.conjB ? -1.0 : 1.0;
+  constexpr int KK = BK / 4;
 
+  constexpr int NCOPY = LA::NPASS + LB::NPASS;
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<ST - 2>();
-    __syncthreads();
-    {
-      const int nk = kt + ST - 1;
-      if (nk < KT) {
-        const int s = nk % ST;
-        la.issue(Ab, (char*)smem + s * STAGE_BYTES, p.gk, nk * BK, p.K, tid);
-        lb.issue(Bb, (char*)smem + s * STAGE_BYTES + A_BYTES, p.gk, nk * BK, p.K, tid);
-      }
-      cp_async_commit();
-    }
+    if (DBG != 3) { cp_async_wait<ST - 2>(); __syncthreads(); }
+    const int nk = kt + ST - 1;
+    const bool more = (DBG == 1 || DBG == 3) ? false : nk < KT;
+    char* nsA = (char*)smem + (nk % ST) * STAGE_BYTES;
+    char* nsB = nsA + A_BYTES;
     const unsigned char* sA = smem + (kt % ST) * STAGE_BYTES;
     const unsigned char* sB = sA + A_BYTES;
+    // copy pass c of the tile ST-1 ahead (A passes first, then B)
+    if (more) { la.begin(p.gk, nk * BK, p.K, tid); lb.begin(p.gk, nk * BK, p.K, tid); }
+    auto copy_pass = [&](int c) {
+      if (c < LA::NPASS) la.issue(c, Ab, nsA, tid);
+      else lb.issue(c - LA::NPASS, Bb, nsB, tid);
+    };
     if (!CPLX) {
       const double* As = (const double*)sA;
       const double* Bs = (const double*)sB;
-#pragma unroll
-      for (int kk = 0; kk < BK / 4; ++kk) {
-        double a[MI], b[NI];
+      double a[2][MI], b[2][NI];
+      auto ldfrag = [&](int kk, double* fa, double* fb) {
         const int k = kk * 4 + lc;
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           const int r = wm0 + i * 8 + lr;
-          a[i] = AK ? As[r * GA::PK + k] : As[k * GA::PR + r];
+          fa[i] = AK ? As[r * GA::PK + k] : As[k * GA::PR + r];
         }
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
           const int r = wn0 + j * 8 + lr;
-          b[j] = BKM ? Bs[r * GB::PK + k] : Bs[k * GB::PR + r];
+          fb[j] = BKM ? Bs[r * GB::PK + k] : Bs[k * GB::PR + r];
         }
+      };
+      constexpr int TOT = MI * NI;   // DMMAs of one k-step per warp
+      if (DBG != 2 || kt == 0) ldfrag(0, a[0], b[0]);
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        if (kk + 1 < KK && (DBG != 2 || kt == 0)) ldfrag(kk + 1, a[(kk + 1) & 1], b[(kk + 1) & 1]);
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
-          for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < NI; ++j) {
+            dmma(acc[i][j][0], acc[i][j][1], a[kk & 1][i], b[kk & 1][j]);
+            if (kk == KK - 1) {   // copies ride in the last k-step, after all fragment loads of this tile
+              const int q = i * NI + j;
+              const int c0 = q * NCOPY / TOT, c1 = (q + 1) * NCOPY / TOT;
+              if (more && c1 > c0) {
+#pragma unroll
+                for (int c = c0; c < c1; ++c) copy_pass(c);
+              }
+            }
+          }
       }
     } else {
       const double2* As = (const double2*)sA;
       const double2* Bs = (const double2*)sB;
-#pragma unroll
-      for (int kk = 0; kk < BK / 4; ++kk) {
-        double2 a[MI], b[NI];
+      double2 a[2][MI], b[2][NI];
+      auto ldfrag = [&](int kk, double2* fa, double2* fb) {
         const int k = kk * 4 + lc;
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           const int r = wm0 + i * 8 + lr;
-          a[i] = AK ? As[r * GA::PK + k] : As[k * GA::PR + r];
-          a[i].y *= sa;
+          fa[i] = AK ? As[r * GA::PK + k] : As[k * GA::PR + r];
+          fa[i].y *= sa;
         }
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
           const int r = wn0 + j * 8 + lr;
-          b[j] = BKM ? Bs[r * GB::PK + k] : Bs[k * GB::PR + r];
-          b[j].y *= sb;
+          fb[j] = BKM ? Bs[r * GB::PK + k] : Bs[k * GB::PR + r];
+          fb[j].y *= sb;
         }
+      };
+      constexpr int TOT = MI * NI;   // complex DMMA quads of one k-step per warp
+      ldfrag(0, a[0], b[0]);
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        if (kk + 1 < KK) ldfrag(kk + 1, a[(kk + 1) & 1], b[(kk + 1) & 1]);
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
-          const double nai = -a[i].y;
+          const double2 av = a[kk & 1][i];
+          const double nai = -av.y;
 #pragma unroll
           for (int j = 0; j < NI; ++j) {
-            dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-            dmma(acc[i][j][0], acc[i][j][1], nai, b[j].y);
-            dmma(acc[i][j][2], acc[i][j][3], a[i].x, b[j].y);
-            dmma(acc[i][j][2], acc[i][j][3], a[i].y, b[j].x);
+            const double2 bv = b[kk & 1][j];
+            dmma(acc[i][j][0], acc[i][j][1], av.x, bv.x);
+            dmma(acc[i][j][0], acc[i][j][1], nai, bv.y);
+            dmma(acc[i][j][2], acc[i][j][3], av.x, bv.y);
+            dmma(acc[i][j][2], acc[i][j][3], av.y, bv.x);
+            if (kk == KK - 1) {
+              const int q = i * NI + j;
+              const int c0 = q * NCOPY / TOT, c1 = (q + 1) * NCOPY / TOT;
+              if (more && c1 > c0) {
+#pragma unroll
+                for (int c = c0; c < c1; ++c) copy_pass(c);
+              }
+            }
           }
         }
       }
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -331,15 +375,19 @@ __global__ void __launch_bounds__(CFG::NT, 1) contract_kernel(const __grid_const
 // ------------------------------------------------------------------------------------
 // host side: launch
 // ------------------------------------------------------------------------------------
-using CfgR = Cfg<128, 128, 16, 32, 64, 4>;   // real:    8 warps, warp tile 32x64
-using CfgRS = Cfg<64, 64, 16, 32, 32, 4>;    // real, small problems: 4 warps, 32x32
-using CfgC = Cfg<128, 64, 8, 32, 32, 4>;     // complex: 8 warps, warp tile 32x32
-using CfgCS = Cfg<64, 32, 8, 32, 16, 4>;     // complex small: 4 warps
+// Two independent 4-warp CTAs per SM: their barrier / copy phases drift apart, so one CTA's
+// DMMA stream covers the other's bubbles (a single 8-warp CTA measured 83% DMMA-pipe
+// utilisation; see profiles/).
+using CfgR = Cfg<64, 128, 16, 32, 64, 3, 2>;    // real:    4 warps, warp tile 32x64, 2 CTAs/SM
+using CfgR1 = Cfg<128, 128, 16, 32, 64, 4, 1>;  // real, one 8-warp CTA/SM (tuning knob TNB_CFG=1)
+using CfgRS = Cfg<64, 64, 16, 32, 32, 3, 2>;    // real, small problems: warp tile 32x32
+using CfgC = Cfg<64, 64, 8, 32, 32, 3, 2>;      // complex: 4 warps, warp tile 32x32, 2 CTAs/SM
+using CfgCS = Cfg<64, 32, 8, 32, 16, 3, 2>;     // complex small
 
 template <bool CPLX, class CFG>
 constexpr int smem_bytes() {
   return CFG::STAGES * (TileGeom<CPLX, CFG::BM, CFG::BK>::ELEMS + TileGeom<CPLX, CFG::BN, CFG::BK>::ELEMS) *
-         (CPLX ? 16 : 8);
+             (CPLX ? 16 : 8);
 }
 
 template <bool CPLX, bool AK, bool BKM, int VA, int VB, class CFG>
@@ -422,6 +470,20 @@ static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) 
   if (!cplx) {
     const bool small = ntiles(CfgR::BM, CfgR::BN) < h->num_sms || p.M <= 64 || p.N <= 64;
     if (small) return launch_cfg<false, CfgRS>(h, p, ak, bk, va, vb, st);
+    static const int tune = getenv("TNB_CFG") ? atoi(getenv("TNB_CFG")) : 0;
+    static const int dbg = getenv("TNB_DBG") ? atoi(getenv("TNB_DBG")) : 0;
+    if (dbg && ak && bk && va == 2 && vb == 2) {  // timing experiments only (results are wrong)
+      p.tilesM = (p.M + CfgR::BM - 1) / CfgR::BM; p.tilesN = (p.N + CfgR::BN - 1) / CfgR::BN; p.groupM = 16;
+      constexpr int SM = smem_bytes<false, CfgR>();
+      auto k1 = contract_kernel<false, true, true, 2, 2, CfgR, 1>;
+      auto k2 = contract_kernel<false, true, true, 2, 2, CfgR, 2>;
+      auto k3 = contract_kernel<false, true, true, 2, 2, CfgR, 3>;
+      auto kk = dbg == 1 ? k1 : dbg == 2 ? k2 : k3;
+      cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+      kk<<<p.tilesM * p.tilesN, CfgR::NT, SM, st>>>(p);
+      return check_cuda(h, cudaGetLastError(), "dbg launch");
+    }
+    if (tune == 1) return launch_cfg<false, CfgR1>(h, p, ak, bk, va, vb, st);
     return launch_cfg<false, CfgR>(h, p, ak, bk, va, vb, st);
   } else {
     const bool small = ntiles(CfgC::BM, CfgC::BN) < h->num_sms || p.M <= 64 || p.N <= 32;

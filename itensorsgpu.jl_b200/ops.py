@@ -161,7 +161,7 @@ def permute_axpby(A, la, B, lb, alpha=1.0, beta=0.0):
     if A.dtype != B.dtype:
         raise TypeError("dtype mismatch")
     la, lb = list(la), list(lb)
-    if sorted(map(repr, la)) != sorted(map(repr, lb)):
+    if len(la) != len(lb) or set(la) != set(lb):
         raise _lib.TnbError(1, "permute: label sets differ")
     ids = {l: i for i, l in enumerate(la)}
     want = tuple(A.dims[la.index(l)] for l in lb)
