@@ -208,8 +208,10 @@ int tnb_factorize_bond(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, voi
                        int64_t* n_keep, double* truncerr, void* stream);
 
 /* One full two-site DMRG bond update: phi = A1*A2; Lanczos; optional noise; factorize.
- * A1/A2 are overwritten (buffers sized for kmax). */
-int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
+ * In: A1[chiL,d1,chiM], A2[chiM,d2,chiR].  Out (overwritten): A1[chiL,d1,k], A2[k,d2,chiR] with
+ * k = *n_keep; both buffers must hold max(input, chiL*d1*kmax / kmax*d2*chiR) elements,
+ * kmax = min(chiL*d1, d2*chiR, maxdim). */
+int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int64_t chiM, const void* L,
                        const void* W1, const void* W2, const void* R, void* A1, void* A2,
                        int ortho, int which_decomp, int64_t maxdim, int64_t mindim,
                        double cutoff, double noise, int krylovdim, int maxiter,

@@ -67,7 +67,7 @@ SIGNATURES = {
     "tnb_noise_term": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _int, _dbl, _int, _vp, _vp]),
     "tnb_factorize_bond": (_int, [_vp, _int, _pbd, _vp, _int, _int, _i64, _i64, _dbl, _vp, _int, _vp, _vp, _pi64,
                                   _pdbl, _vp]),
-    "tnb_dmrg_bond_step": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _i64, _dbl, _dbl,
+    "tnb_dmrg_bond_step": (_int, [_vp, _int, _pbd, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _i64, _dbl, _dbl,
                                   _int, _int, _pdbl, _pi64, _pdbl, _vp]),
     "tnb_tebd_apply_gate": (_int, [_vp, _int, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _dbl, _pi64,
                                    _pdbl, _vp]),

@@ -21,8 +21,9 @@ int check_cuda(Handle* h, cudaError_t e, const char* what) {
 }
 
 int ws_require(Handle* h, size_t bytes) {
+  bytes += h->ws_base;
   if (bytes <= h->ws_bytes) return TNB_OK;
-  if (h->ws_off != 0)
+  if (h->ws_off != 0 || h->ws_base != 0)
     return set_err(h, TNB_ERR_ALLOC, "internal: workspace growth requested while in use (%zu > %zu)", bytes,
                    h->ws_bytes);
   TNB_CUDA(h, cudaDeviceSynchronize());
@@ -47,7 +48,7 @@ int ws_require(Handle* h, size_t bytes) {
 int ws_alloc(Handle* h, size_t bytes, void** out) {
   size_t off = (h->ws_off + 255) & ~(size_t)255;
   if (off + bytes > h->ws_bytes) {
-    if (h->ws_off != 0)
+    if (h->ws_off != 0 || h->ws_base != 0)
       return set_err(h, TNB_ERR_ALLOC, "internal: workspace exhausted (%zu + %zu > %zu); ws_require missing",
                      off, bytes, h->ws_bytes);
     TNB_TRY(ws_require(h, off + bytes));

@@ -198,6 +198,13 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
 
   const char* Ab = (const char*)p.A;
   const char* Bb = (const char*)p.B;
+  char* Cb = (char*)p.C;
+  if (p.batch > 1 || p.boffA || p.boffB || p.boffC) {
+    const int bz = blockIdx.y;
+    Ab += (p.boffA ? p.boffA[bz] : bz * p.bstrideA) * EB;
+    Bb += (p.boffB ? p.boffB[bz] : bz * p.bstrideB) * EB;
+    Cb += (p.boffC ? p.boffC[bz] : bz * p.bstrideC) * EB;
+  }
   const int KT = (p.K + BK - 1) / BK;
 
   double acc[MI][NI][CPLX ? 4 : 2];
@@ -350,12 +357,12 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
       for (int i = 0; i < MI; ++i) {
         if (!okm[i]) continue;
         if (!CPLX) {
-          double* c = (double*)p.C + offm[i] + offn;
+          double* c = (double*)Cb + offm[i] + offn;
           double v = p.alpha_re * acc[i][j][e];
           if (has_beta) v += p.beta_re * (*c);
           *c = v;
         } else {
-          double2* c = (double2*)p.C + offm[i] + offn;
+          double2* c = (double2*)Cb + offm[i] + offn;
           const double xr = acc[i][j][e], xi = acc[i][j][2 + e];
           double2 v;
           v.x = p.alpha_re * xr - p.alpha_im * xi;
@@ -404,7 +411,9 @@ static int launch_one(Handle* h, GemmParams& p, cudaStream_t st) {
   p.groupM = 16;
   const long long tiles = (long long)p.tilesM * p.tilesN;
   if (tiles > 2147483647LL) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: too many tiles");
-  kern<<<(unsigned)tiles, CFG::NT, SM, st>>>(p);
+  if (p.batch < 1) p.batch = 1;
+  if (p.batch > 65535) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: batch > 65535");
+  kern<<<dim3((unsigned)tiles, (unsigned)p.batch), CFG::NT, SM, st>>>(p);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "contract_kernel launch");
 }
@@ -465,8 +474,10 @@ static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) 
           ((uintptr_t)p.B % 16 == 0)) vb = 2;
     }
   }
+  if (!p.boffA && (p.bstrideA & 1)) va = 1;   // batched: 16-byte copies need even element offsets
+  if (!p.boffB && (p.bstrideB & 1)) vb = 1;   // (offset tables must hold even offsets for f64)
   // tile config: big tiles unless they cannot fill the machine
-  auto ntiles = [&](int bm, int bn) { return ((long long)(p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn); };
+  auto ntiles = [&](int bm, int bn) { return ((long long)(p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * std::max(p.batch, 1); };
   if (!cplx) {
     const bool small = ntiles(CfgR::BM, CfgR::BN) < h->num_sms || p.M <= 64 || p.N <= 64;
     if (small) return launch_cfg<false, CfgRS>(h, p, ak, bk, va, vb, st);
@@ -619,14 +630,40 @@ int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, in
   memset(&p, 0, sizeof(p));
   p.gm.n = p.gn.n = p.gk.n = 1;
   p.gm.ext[0] = (int)m; p.gn.ext[0] = (int)n; p.gk.ext[0] = (int)std::max<int64_t>(k, 1);
-  p.gm.sX[0] = (opA == 'N') ? 1 : lda;  p.gk.sX[0] = (opA == 'N') ? lda : 1;
-  p.gn.sX[0] = (opB == 'N') ? ldb : 1;  p.gk.sY[0] = (opB == 'N') ? 1 : ldb;
+  // op: 'N' none, 'T' transpose, 'C' conjugate transpose, 'J' conjugate (no transpose)
+  const bool na = (opA == 'N' || opA == 'J'), nb = (opB == 'N' || opB == 'J');
+  p.gm.sX[0] = na ? 1 : lda;  p.gk.sX[0] = na ? lda : 1;
+  p.gn.sX[0] = nb ? ldb : 1;  p.gk.sY[0] = nb ? 1 : ldb;
   p.gm.sY[0] = 1; p.gn.sY[0] = ldc;
   p.M = (int)m; p.N = (int)n; p.K = (int)std::max<int64_t>(k, 1);
   p.A = A; p.B = B; p.C = C;
   set_scalars(p, dtype, alpha, beta);
   if (k == 0) { p.alpha_re = 0; p.alpha_im = 0; p.gk.sX[0] = 0; p.gk.sY[0] = 0; }
+  p.conjA = (opA == 'C' || opA == 'J'); p.conjB = (opB == 'C' || opB == 'J');
+  return launch_planned(h, dtype, p, st);
+}
+
+int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
+                      const void* alpha, const void* A, int64_t lda, const long long* offA, long long strideA,
+                      const void* B, int64_t ldb, const long long* offB, long long strideB, const void* beta,
+                      void* C, int64_t ldc, const long long* offC, long long strideC, int batch,
+                      cudaStream_t st) {
+  if (m == 0 || n == 0 || batch == 0) return TNB_OK;
+  if (k < 1) return set_err(h, TNB_ERR_BAD_ARG, "gemm_batched: k < 1");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.gm.n = p.gn.n = p.gk.n = 1;
+  p.gm.ext[0] = (int)m; p.gn.ext[0] = (int)n; p.gk.ext[0] = (int)k;
+  p.gm.sX[0] = (opA == 'N') ? 1 : lda;  p.gk.sX[0] = (opA == 'N') ? lda : 1;
+  p.gn.sX[0] = (opB == 'N') ? ldb : 1;  p.gk.sY[0] = (opB == 'N') ? 1 : ldb;
+  p.gm.sY[0] = 1; p.gn.sY[0] = ldc;
+  p.M = (int)m; p.N = (int)n; p.K = (int)k;
+  p.A = A; p.B = B; p.C = C;
+  set_scalars(p, dtype, alpha, beta);
   p.conjA = opA == 'C'; p.conjB = opB == 'C';
+  p.batch = batch;
+  p.boffA = offA; p.boffB = offB; p.boffC = offC;
+  p.bstrideA = strideA; p.bstrideB = strideB; p.bstrideC = strideC;
   return launch_planned(h, dtype, p, st);
 }
 

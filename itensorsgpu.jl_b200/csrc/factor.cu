@@ -1,5 +1,215 @@
-// Factorizations (svd / eigh / qr) and the bond-level entry points built on them.
+// Public factorization entry points (svd / eigh / qr with truncation) and the bond-level
+// operations built on them: factorize (replacebond!), one full DMRG bond step, TEBD gate step.
+//
+// [EXT] ITensors `factorize` / `replacebond!` / `apply` sequence the reference's svd / eigen / qr
+// overrides (/root/reference/src/tensor/culinearalgebra.jl:33-121) and truncate!
+// (src/tensor/cutruncate.jl:1-93); here the whole sequence is one C call with one sync.
 #include "tnb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace tnb {
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+__global__ void square_kernel(const double* __restrict__ s, double* p, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = s[i] * s[i];
+}
+
+// out (k x n, ld k) <- diag(s) * V^T  with V (n x kmaxv, ldv): out[i,j] = s_i * V[j,i]   (s may be null -> 1)
+template <typename T>
+__global__ void sv_transpose_kernel(T* out, long long k, long long n, const T* __restrict__ V, long long ldv,
+                                    const double* __restrict__ s) {
+  __shared__ T tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i0 = (long long)blockIdx.x * 32, j0 = (long long)blockIdx.y * 32;
+  for (int yy = 0; yy < 32; yy += 8) {
+    const long long j = j0 + tx, i = i0 + ty + yy;   // read V[j, i] coalesced along j
+    if (i < k && j < n) tile[ty + yy][tx] = V[j + i * ldv];
+  }
+  __syncthreads();
+  for (int yy = 0; yy < 32; yy += 8) {
+    const long long i = i0 + tx, j = j0 + ty + yy;
+    if (i < k && j < n) {
+      T v = tile[tx][ty + yy];
+      const double f = s ? s[i] : 1.0;
+      if constexpr (sizeof(T) == 16) { v.x *= f; v.y *= f; } else v *= f;
+      out[i + j * k] = v;
+    }
+  }
+}
+
+// X (m x k, ld m): column j scaled by s_j
+template <typename T>
+__global__ void scale_columns_kernel(T* X, long long m, long long k, const double* __restrict__ s) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < m * k; e += (long long)gridDim.x * blockDim.x) {
+    const double f = s[e / m];
+    if constexpr (sizeof(T) == 16) { X[e].x *= f; X[e].y *= f; } else X[e] *= f;
+  }
+}
+
+static int sv_transpose(Handle* h, int dtype, void* out, int64_t k, int64_t n, const void* V, int64_t ldv, const double* s,
+                        cudaStream_t st) {
+  if (k == 0 || n == 0) return TNB_OK;
+  dim3 g((unsigned)((k + 31) / 32), (unsigned)((n + 31) / 32));
+  if (g.y > 65535) return set_err(h, TNB_ERR_UNSUPPORTED, "sv_transpose: n too large");
+  if (dtype == TNB_C128) sv_transpose_kernel<double2><<<g, 256, 0, st>>>((double2*)out, k, n, (const double2*)V, ldv, s);
+  else sv_transpose_kernel<double><<<g, 256, 0, st>>>((double*)out, k, n, (const double*)V, ldv, s);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "sv_transpose");
+}
+
+static int scale_columns(Handle* h, int dtype, void* X, int64_t m, int64_t k, const double* s, cudaStream_t st) {
+  if (m * k == 0) return TNB_OK;
+  const int g = h->num_sms * 4;
+  if (dtype == TNB_C128) scale_columns_kernel<double2><<<g, 256, 0, st>>>((double2*)X, m, k, s);
+  else scale_columns_kernel<double><<<g, 256, 0, st>>>((double*)X, m, k, s);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "scale_columns");
+}
+
+// ---- truncated svd into arena-or-caller buffers.  Arena must already be sized.
+static int svd_trunc_core(Handle* h, int dtype, int64_t m, int64_t n, const void* A, int64_t maxdim, int64_t mindim,
+                          double cutoff, int flags, int do_truncate, void* U, double* S, void* V, int64_t* n_keep,
+                          double* truncerr, cudaStream_t st) {
+  const int64_t kfull = std::min(m, n);
+  int64_t kmax = kfull;
+  if (do_truncate && maxdim > 0) kmax = std::min(kfull, maxdim);
+  void *Sall, *P;
+  TNB_TRY(ws_alloc(h, kfull * sizeof(double), &Sall));
+  TNB_TRY(ws_alloc(h, kfull * sizeof(double), &P));
+  TNB_TRY(svd_impl(h, dtype, m, n, A, m, kmax, kfull, U, m, (double*)Sall, V, n, st));
+  int64_t nk = kfull;
+  double err = 0.0;
+  if (do_truncate) {
+    square_kernel<<<std::max(1, (int)((kfull + 255) / 256)), 256, 0, st>>>((const double*)Sall, (double*)P, (int)kfull);
+    h->launches++;
+    double docut;
+    TNB_TRY(truncate_impl(h, (const double*)P, kfull, maxdim > 0 ? maxdim : kfull, mindim, cutoff, flags, &nk, &err, &docut, st));
+  }
+  TNB_CUDA(h, cudaMemcpyAsync(S, Sall, kmax * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (n_keep) *n_keep = nk;
+  if (truncerr) *truncerr = err;
+  return TNB_OK;
+}
+
+static int eigh_trunc_core(Handle* h, int dtype, int64_t n, void* A, int64_t maxdim, int64_t mindim, double cutoff,
+                           int flags, int do_truncate, double* D, void* U, int64_t* n_keep, double* truncerr,
+                           cudaStream_t st) {
+  int64_t kmax = n;
+  if (do_truncate && maxdim > 0) kmax = std::min(n, maxdim);
+  void* Dall;
+  TNB_TRY(ws_alloc(h, n * sizeof(double), &Dall));
+  TNB_TRY(eigh_impl(h, dtype, n, A, kmax, n, (double*)Dall, U, n, st));
+  int64_t nk = n;
+  double err = 0.0;
+  if (do_truncate) {
+    double docut;
+    TNB_TRY(truncate_impl(h, (const double*)Dall, n, maxdim > 0 ? maxdim : n, mindim, cutoff, flags, &nk, &err, &docut, st));
+  }
+  TNB_CUDA(h, cudaMemcpyAsync(D, Dall, kmax * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (n_keep) *n_keep = nk;
+  if (truncerr) *truncerr = err;
+  return TNB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// factorize a bond: M (m x n) = phi[(l,s1),(s2,r)] -> A (m x k), B (k x n)
+// ------------------------------------------------------------------------------------
+static size_t factorize_ws_bytes(int dtype, int64_t m, int64_t n) {
+  const size_t es = elsize(dtype);
+  const int64_t mx = std::max(m, n);
+  size_t t = std::max({svd_ws_bytes(dtype, m, n), eigh_ws_bytes(dtype, mx), qr_ws_bytes(dtype, m, n), qr_ws_bytes(dtype, n, m)});
+  t += 3 * al256((size_t)mx * mx * es);          // rho / U / V / transposed copies
+  t += 4 * al256((size_t)mx * sizeof(double));
+  return t + (1 << 16);
+}
+
+static int factorize_core(Handle* h, int dtype, int64_t m, int64_t n, void* M, int ortho, int which, int64_t maxdim,
+                          int64_t mindim, double cutoff, const void* rho_pert, int normalize, void* A, void* B,
+                          int64_t* n_keep, double* truncerr, cudaStream_t st) {
+  const size_t es = elsize(dtype);
+  const int64_t kfull = std::min(m, n);
+  const bool trunc = true;
+  if (which == TNB_DECOMP_AUTO) {
+    if (rho_pert) which = TNB_DECOMP_EIGEN;
+    else which = (cutoff <= 1e-12) ? TNB_DECOMP_SVD : TNB_DECOMP_EIGEN;
+  }
+  int64_t nk = kfull;
+  double err = 0.0;
+  double one[2] = {1.0, 0.0};
+  if (which == TNB_DECOMP_SVD) {
+    int64_t kmax = maxdim > 0 ? std::min(kfull, maxdim) : kfull;
+    void *U, *V, *S;
+    TNB_TRY(ws_alloc(h, (size_t)m * kmax * es, &U));
+    TNB_TRY(ws_alloc(h, (size_t)n * kmax * es, &V));
+    TNB_TRY(ws_alloc(h, (size_t)kmax * sizeof(double), &S));
+    TNB_TRY(svd_trunc_core(h, dtype, m, n, M, maxdim, mindim, cutoff, 0, trunc, U, (double*)S, V, &nk, &err, st));
+    TNB_CUDA(h, cudaMemcpyAsync(A, U, (size_t)m * nk * es, cudaMemcpyDeviceToDevice, st));
+    if (ortho == TNB_ORTHO_LEFT) {
+      TNB_TRY(sv_transpose(h, dtype, B, nk, n, V, n, (const double*)S, st));
+    } else {
+      TNB_TRY(scale_columns(h, dtype, A, m, nk, (const double*)S, st));
+      TNB_TRY(sv_transpose(h, dtype, B, nk, n, V, n, nullptr, st));
+    }
+  } else if (which == TNB_DECOMP_EIGEN) {
+    const int64_t r = (ortho == TNB_ORTHO_LEFT) ? m : n;
+    int64_t kmax = maxdim > 0 ? std::min(r, maxdim) : r;
+    void *rho, *U, *D;
+    TNB_TRY(ws_alloc(h, (size_t)r * r * es, &rho));
+    TNB_TRY(ws_alloc(h, (size_t)r * kmax * es, &U));
+    TNB_TRY(ws_alloc(h, (size_t)kmax * sizeof(double), &D));
+    if (rho_pert) TNB_CUDA(h, cudaMemcpyAsync(rho, rho_pert, (size_t)r * r * es, cudaMemcpyDeviceToDevice, st));
+    const void* beta = rho_pert ? one : nullptr;
+    if (ortho == TNB_ORTHO_LEFT) {
+      // rho = M M^H (+ pert)
+      TNB_TRY(gemm_impl(h, dtype, 'N', 'C', m, m, n, nullptr, M, m, M, m, beta, rho, m, st));
+      TNB_TRY(eigh_trunc_core(h, dtype, m, rho, maxdim, mindim, cutoff, 0, trunc, (double*)D, U, &nk, &err, st));
+      TNB_CUDA(h, cudaMemcpyAsync(A, U, (size_t)m * nk * es, cudaMemcpyDeviceToDevice, st));
+      // B = U^H M
+      TNB_TRY(gemm_impl(h, dtype, 'C', 'N', nk, n, m, nullptr, U, m, M, m, nullptr, B, nk, st));
+    } else {
+      // rho[j,j'] = sum_i M[i,j] conj(M[i,j'])  = M^T conj(M) (+ pert)
+      TNB_TRY(gemm_impl(h, dtype, 'T', 'J', n, n, m, nullptr, M, m, M, m, beta, rho, n, st));
+      TNB_TRY(eigh_trunc_core(h, dtype, n, rho, maxdim, mindim, cutoff, 0, trunc, (double*)D, U, &nk, &err, st));
+      // A = M conj(U) (m x nk) ; B = U^T (nk x n)
+      TNB_TRY(gemm_impl(h, dtype, 'N', 'J', m, nk, n, nullptr, M, m, U, n, nullptr, A, m, st));
+      TNB_TRY(sv_transpose(h, dtype, B, nk, n, U, n, nullptr, st));
+    }
+  } else if (which == TNB_DECOMP_QR) {
+    nk = kfull;
+    if (ortho == TNB_ORTHO_LEFT) {
+      TNB_TRY(qr_impl(h, dtype, m, n, M, A, B, st));
+    } else {
+      // M^T = Q R  =>  M = R^T Q^T : A = R^T (m x k), B = Q^T (k x n)
+      void *Mt, *Q, *R;
+      TNB_TRY(ws_alloc(h, (size_t)m * n * es, &Mt));
+      TNB_TRY(ws_alloc(h, (size_t)n * kfull * es, &Q));
+      TNB_TRY(ws_alloc(h, (size_t)kfull * m * es, &R));
+      TNB_TRY(sv_transpose(h, dtype, Mt, n, m, M, m, nullptr, st));     // Mt (n x m) = M^T
+      TNB_TRY(qr_impl(h, dtype, n, m, Mt, Q, R, st));
+      TNB_TRY(sv_transpose(h, dtype, A, m, kfull, R, kfull, nullptr, st));
+      TNB_TRY(sv_transpose(h, dtype, B, kfull, n, Q, n, nullptr, st));
+    }
+  } else {
+    return set_err(h, TNB_ERR_BAD_ARG, "factorize: which_decomp %d", which);
+  }
+  if (normalize) {
+    if (ortho == TNB_ORTHO_LEFT) {
+      TNB_TRY(nrm2_impl(h, dtype, nk * n, B, h->scal + 120, st));
+      TNB_TRY(scale_inv_dev_impl(h, dtype, nk * n, B, B, h->scal + 120, 0.0, st));
+    } else {
+      TNB_TRY(nrm2_impl(h, dtype, m * nk, A, h->scal + 120, st));
+      TNB_TRY(scale_inv_dev_impl(h, dtype, m * nk, A, A, h->scal + 120, 0.0, st));
+    }
+  }
+  if (n_keep) *n_keep = nk;
+  if (truncerr) *truncerr = err;
+  return TNB_OK;
+}
+
+}  // namespace tnb
 
 using namespace tnb;
 #define H ((Handle*)h)
@@ -11,35 +221,137 @@ int tnb_svd_trunc(tnb_handle_t h, int dtype, int64_t m, int64_t n, void* A, int6
                   double cutoff, int flags, int do_truncate, void* U, double* S, void* V, int64_t* n_keep,
                   double* truncerr, void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
-  return set_err(H, TNB_ERR_UNSUPPORTED, "svd_trunc: not built yet");
+  if (!A || !U || !S || !V || m < 1 || n < 1) return set_err(H, TNB_ERR_BAD_ARG, "svd_trunc: bad argument");
+  ws_reset(H);
+  TNB_TRY(ws_require(H, svd_ws_bytes(dtype, m, n) + 2 * al256(std::min(m, n) * 8) + 4096));
+  TNB_TRY(svd_trunc_core(H, dtype, m, n, A, maxdim, mindim, cutoff, flags, do_truncate, U, S, V, n_keep, truncerr, ST));
+  return check_cuda(H, cudaStreamSynchronize(ST), "svd_trunc sync");
 }
+
 int tnb_eigh_trunc(tnb_handle_t h, int dtype, int64_t n, void* A, int64_t maxdim, int64_t mindim, double cutoff,
                    int flags, int do_truncate, double* D, void* U, int64_t* n_keep, double* truncerr,
                    void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
-  return set_err(H, TNB_ERR_UNSUPPORTED, "eigh_trunc: not built yet");
+  if (!A || !D || !U || n < 1) return set_err(H, TNB_ERR_BAD_ARG, "eigh_trunc: bad argument");
+  ws_reset(H);
+  TNB_TRY(ws_require(H, eigh_ws_bytes(dtype, n) + al256(n * 8) + 4096));
+  TNB_TRY(eigh_trunc_core(H, dtype, n, A, maxdim, mindim, cutoff, flags, do_truncate, D, U, n_keep, truncerr, ST));
+  return check_cuda(H, cudaStreamSynchronize(ST), "eigh_trunc sync");
 }
+
 int tnb_qr(tnb_handle_t h, int dtype, int64_t m, int64_t n, const void* A, void* Q, void* R, void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
-  return set_err(H, TNB_ERR_UNSUPPORTED, "qr: not built yet");
+  if (!A || !Q || !R) return set_err(H, TNB_ERR_BAD_ARG, "qr: null pointer");
+  ws_reset(H);
+  TNB_TRY(ws_require(H, qr_ws_bytes(dtype, m, n)));
+  return qr_impl(H, dtype, m, n, A, Q, R, ST);
 }
-int tnb_factorize_bond(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, void* phi, int ortho,
-                       int which_decomp, int64_t maxdim, int64_t mindim, double cutoff, const void* rho_pert,
-                       int normalize, void* A, void* B, int64_t* n_keep, double* truncerr, void* stream) {
+
+int tnb_factorize_bond(tnb_handle_t h, int dtype, const tnb_bond_dims* d, void* phi, int ortho, int which_decomp,
+                       int64_t maxdim, int64_t mindim, double cutoff, const void* rho_pert, int normalize, void* A,
+                       void* B, int64_t* n_keep, double* truncerr, void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
-  return set_err(H, TNB_ERR_UNSUPPORTED, "factorize_bond: not built yet");
+  if (!d || !phi || !A || !B) return set_err(H, TNB_ERR_BAD_ARG, "factorize_bond: null pointer");
+  const int64_t m = d->chiL * d->d1, n = (int64_t)d->d2 * d->chiR;
+  ws_reset(H);
+  TNB_TRY(ws_require(H, factorize_ws_bytes(dtype, m, n)));
+  TNB_TRY(factorize_core(H, dtype, m, n, phi, ortho, which_decomp, maxdim, mindim, cutoff, rho_pert, normalize, A, B,
+                         n_keep, truncerr, ST));
+  return check_cuda(H, cudaStreamSynchronize(ST), "factorize_bond sync");
 }
-int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,
+
+int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* d, int64_t chiM, const void* L, const void* W1,
                        const void* W2, const void* R, void* A1, void* A2, int ortho, int which_decomp,
                        int64_t maxdim, int64_t mindim, double cutoff, double noise, int krylovdim, int maxiter,
                        double* energy, int64_t* n_keep, double* truncerr, void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
-  return set_err(H, TNB_ERR_UNSUPPORTED, "dmrg_bond_step: not built yet");
+  if (!d || !L || !W1 || !W2 || !R || !A1 || !A2) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_bond_step: null pointer");
+  if (chiM < 1) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_bond_step: chiM < 1");
+  const size_t es = elsize(dtype);
+  const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2;
+  const int64_t m = cl * d1, n = d2 * cr;
+  const size_t phib = al256((size_t)m * n * es);
+  const int64_t r = (ortho == TNB_ORTHO_LEFT) ? m : n;
+  // phi and (optionally) the noise perturbation live in caller-independent device scratch that must
+  // survive the Lanczos and factorize arena resets -> allocate them at the very start of the arena
+  // and make every later stage allocate after them (no ws_reset in between).
+  const size_t lan = heff_workspace_bytes(dtype, d) + (size_t)(krylovdim + 1) * phib + (1 << 16);
+  const size_t fac = (size_t)0;
+  (void)fac;
+  size_t need = phib + (noise > 0 ? al256((size_t)r * r * es) : 0);
+  size_t stage = std::max<size_t>(lan, 0);
+  // factorize workspace (recomputed with the same formula as tnb_factorize_bond)
+  {
+    const int64_t mx = std::max(m, n);
+    size_t t = std::max({svd_ws_bytes(dtype, m, n), eigh_ws_bytes(dtype, mx), qr_ws_bytes(dtype, m, n), qr_ws_bytes(dtype, n, m)});
+    t += 3 * al256((size_t)mx * mx * es) + 4 * al256((size_t)mx * sizeof(double)) + (1 << 16);
+    stage = std::max(stage, t);
+  }
+  ws_reset(H);
+  TNB_TRY(ws_require(H, need + stage + (1 << 16)));
+  void *phi, *rho = nullptr;
+  TNB_TRY(ws_alloc(H, (size_t)m * n * es, &phi));
+  if (noise > 0) TNB_TRY(ws_alloc(H, (size_t)r * r * es, &rho));
+  const size_t mark = H->ws_off;
+  {  // phi[l,s1,s2,r] = A1[l,s1,k] A2[k,s2,r]
+    TNB_TRY(gemm_impl(H, dtype, 'N', 'N', m, n, chiM, nullptr, A1, m, A2, chiM, nullptr, phi, m, ST));
+  }
+  // Inner stages reset the arena to `ws_base`, so phi / rho at the front stay pinned.
+  {
+    int nmv = 0;
+    H->ws_base = mark;
+    int rc = lanczos_impl(H, dtype, d, L, W1, W2, R, phi, krylovdim, maxiter, 1e-14, energy, &nmv, ST);
+    if (!rc && noise > 0) {
+      ws_reset(H);
+      const size_t hw = heff_workspace_bytes(dtype, d);
+      void *t0, *t1;
+      rc = ws_alloc(H, hw / 2, &t0);
+      if (!rc) rc = ws_alloc(H, hw / 2, &t1);
+      if (!rc) rc = noise_term_impl(H, dtype, d, L, W1, W2, R, phi, ortho, noise, 0, rho, t0, t1, ST);
+    }
+    if (!rc) {
+      ws_reset(H);
+      rc = factorize_core(H, dtype, m, n, phi, ortho, which_decomp, maxdim, mindim, cutoff, rho, 1, A1, A2, n_keep,
+                          truncerr, ST);
+    }
+    H->ws_base = 0;
+    ws_reset(H);
+    if (rc) return rc;
+  }
+  return check_cuda(H, cudaStreamSynchronize(ST), "dmrg_bond_step sync");
 }
-int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR, int32_t d1,
-                        int32_t d2, const void* G, void* A1, void* A2, int64_t maxdim, int64_t mindim,
-                        double cutoff, int64_t* n_keep, double* truncerr, void* stream) {
+
+int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR, int32_t d1, int32_t d2,
+                        const void* G, void* A1, void* A2, int64_t maxdim, int64_t mindim, double cutoff,
+                        int64_t* n_keep, double* truncerr, void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
-  return set_err(H, TNB_ERR_UNSUPPORTED, "tebd_apply_gate: not built yet");
+  if (!G || !A1 || !A2) return set_err(H, TNB_ERR_BAD_ARG, "tebd_apply_gate: null pointer");
+  if (chiL < 1 || chiM < 1 || chiR < 1 || d1 < 1 || d2 < 1) return set_err(H, TNB_ERR_BAD_ARG, "tebd_apply_gate: dims");
+  const size_t es = elsize(dtype);
+  const int64_t m = chiL * d1, n = (int64_t)d2 * chiR;
+  const size_t phib = al256((size_t)m * n * es);
+  size_t fac;
+  {
+    const int64_t mx = std::max(m, n);
+    fac = std::max({svd_ws_bytes(dtype, m, n), eigh_ws_bytes(dtype, mx), qr_ws_bytes(dtype, m, n), qr_ws_bytes(dtype, n, m)});
+    fac += 3 * al256((size_t)mx * mx * es) + 4 * al256((size_t)mx * sizeof(double)) + (1 << 16);
+  }
+  ws_reset(H);
+  TNB_TRY(ws_require(H, 2 * phib + fac + (1 << 16)));
+  void *theta, *theta2;
+  TNB_TRY(ws_alloc(H, (size_t)m * n * es, &theta));
+  TNB_TRY(ws_alloc(H, (size_t)m * n * es, &theta2));
+  TNB_TRY(gemm_impl(H, dtype, 'N', 'N', m, n, chiM, nullptr, A1, m, A2, chiM, nullptr, theta, m, ST));
+  {  // theta2[l,s1',s2',r] = G[s1',s2',s1,s2] theta[l,s1,s2,r]
+    enum { l = 0, s1, s2, r, s1p, s2p };
+    int64_t ea[] = {chiL, d1, d2, chiR}; int32_t ma[] = {l, s1, s2, r};
+    int64_t eb[] = {d1, d2, d1, d2};     int32_t mb[] = {s1p, s2p, s1, s2};
+    int64_t ec[] = {chiL, d1, d2, chiR}; int32_t mc[] = {l, s1p, s2p, r};
+    TNB_TRY(contract_impl(H, dtype, 4, ea, ma, theta, 4, eb, mb, G, 4, ec, mc, theta2, nullptr, nullptr, 0, ST));
+  }
+  TNB_TRY(factorize_core(H, dtype, m, n, theta2, TNB_ORTHO_LEFT, TNB_DECOMP_AUTO, maxdim, mindim, cutoff, nullptr, 0, A1,
+                         A2, n_keep, truncerr, ST));
+  return check_cuda(H, cudaStreamSynchronize(ST), "tebd_apply_gate sync");
 }
-}
+
+}  // extern "C"

@@ -1,0 +1,523 @@
+// Blocked one-sided Jacobi (Hestenes) SVD and Hermitian eigendecomposition.
+//
+// Replaces `svd(::CuDenseTensor{_,2})` -> CUSOLVER.svd! (gesvd) and
+// `eigen(::Hermitian{CuDenseTensor})` -> syevd!/heevd! + reverse + slice copies
+// (/root/reference/src/tensor/culinearalgebra.jl:33-72, 74-108).
+//
+// Algorithm: the columns of G (= A, later A*V) are split into blocks of b columns that sit in
+// "slots"; slots 2p and 2p+1 form pair p.  One step = for every pair at once
+//   1. Gram      S_p = X_p^H X_p,  X_p = [G_slot(2p) G_slot(2p+1)]   (batched DMMA GEMM, K = m)
+//   2. diagonalise S_p = W_p L W_p^H  (2b x 2b, two-sided cyclic Jacobi in shared memory, 1 CTA)
+//   3. rotate    G' = X_p W_p,  V' = V_p W_p                        (batched DMMA GEMM, K = 2b)
+// and step 3 writes each half to the slot it must occupy in the NEXT step of the round-robin
+// tournament, so the data motion of the pairing is fused into the GEMM epilogue and every step
+// uses the same offset tables.  nblk-1 steps = one sweep (all pairs met); sweeps repeat until the
+// largest normalised off-diagonal Gram entry seen in a sweep is below tol.  All O(m n^2) work
+// is in the DMMA contraction kernel; singular values are the final column norms.
+#include "tnb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+namespace tnb {
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <bool CPLX> struct JT { using T = double; static constexpr int NB2 = 112; };
+template <> struct JT<true> { using T = double2; static constexpr int NB2 = 80; };
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) { /* conj(a)*b */ return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+
+// ------------------------------------------------------------------------------------
+// small Hermitian eigensolver: one CTA per matrix, S and W resident in shared memory
+// ------------------------------------------------------------------------------------
+template <bool CPLX, int N>
+__global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<CPLX>::T* __restrict__ Sg,
+                                                             typename JT<CPLX>::T* __restrict__ Wg,
+                                                             double* offmax, int max_sweeps) {
+  using T = typename JT<CPLX>::T;
+  constexpr int LD = N + 1;
+  constexpr int H = N / 2;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  T* S = (T*)smraw;            // S[j*LD + i] = S(i,j)
+  T* W = S + N * LD;
+  __shared__ double red[32];
+  __shared__ double rot_c[H], rot_s[H];
+  __shared__ double2 rot_ph[H];   // e^{-i theta}
+  __shared__ int flag;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const T* Sin = Sg + (size_t)blockIdx.x * N * N;
+  T* Wout = Wg + (size_t)blockIdx.x * N * N;
+  for (int e = tid; e < N * N; e += nt) {
+    const int i = e % N, j = e / N;
+    S[j * LD + i] = Sin[e];
+    if (CPLX) { double2 w = make_double2(i == j ? 1.0 : 0.0, 0.0); ((double2*)W)[j * LD + i] = w; }
+    else ((double*)W)[j * LD + i] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  auto re = [](T v) -> double { if constexpr (CPLX) return v.x; else return v; };
+  auto abs2 = [](T v) -> double { if constexpr (CPLX) return v.x * v.x + v.y * v.y; else return v * v; };
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    // normalised off-diagonal maximum
+    double mx = 0.0;
+    for (int e = tid; e < N * N; e += nt) {
+      const int i = e % N, j = e / N;
+      if (i < j) {
+        const double d = re(S[i * LD + i]) * re(S[j * LD + j]);
+        const double a = abs2(S[j * LD + i]);
+        if (a > 0.0) mx = fmax(mx, d > 0.0 ? a / d : 1e300);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      double m2 = 0;
+      for (int i = 0; i < (nt >> 5); ++i) m2 = fmax(m2, red[i]);
+      m2 = sqrt(m2);
+      if (sweep == 0 && offmax) {
+        // atomic max on a non-negative double via its bit pattern
+        atomicMax((unsigned long long*)offmax, (unsigned long long)__double_as_longlong(fmin(m2, 1e300)));
+      }
+      flag = (m2 < 1e-15) ? 1 : 0;
+    }
+    __syncthreads();
+    if (flag) break;
+
+    for (int round = 0; round < N - 1; ++round) {
+      // round-robin pairing: position k in [0,H): a = (k==0) ? N-1 : (round+k)%(N-1), b = (round + N-1 - k)%(N-1)
+      if (tid < H) {
+        const int k = tid;
+        int p = (k == 0) ? (N - 1) : (round + k) % (N - 1);
+        int q = (round + (N - 1) - k) % (N - 1);
+        if (p > q) { int t = p; p = q; q = t; }
+        const T spq = S[q * LD + p];
+        const double app = re(S[p * LD + p]), aqq = re(S[q * LD + q]);
+        const double g2 = abs2(spq);
+        double c = 1.0, s = 0.0;
+        double2 ph = make_double2(1.0, 0.0);
+        if (g2 > 0.0 && g2 > 1e-34 * fabs(app * aqq)) {
+          const double g = sqrt(g2);
+          const double tau = (aqq - app) / (2.0 * g);
+          const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+          if constexpr (CPLX) ph = make_double2(spq.x / g, -spq.y / g);   // e^{-i theta}
+          else ph = make_double2(spq >= 0 ? 1.0 : -1.0, 0.0);
+        }
+        rot_c[k] = c; rot_s[k] = s; rot_ph[k] = ph;
+      }
+      __syncthreads();
+      // column phase: X(:,p) <- c X(:,p) - s e^{-i th} X(:,q) ; X(:,q) <- s X(:,p) + c e^{-i th} X(:,q)   for X in {S, W}
+      for (int e = tid; e < H * N * 2; e += nt) {
+        const int i = e % N;
+        const int k = (e / N) % H;
+        const int which = e / (N * H);
+        int p = (k == 0) ? (N - 1) : (round + k) % (N - 1);
+        int q = (round + (N - 1) - k) % (N - 1);
+        if (p > q) { int t = p; p = q; q = t; }
+        const double c = rot_c[k], s = rot_s[k];
+        if (s == 0.0) continue;
+        T* X = which ? W : S;
+        const T xp = X[p * LD + i], xq = X[q * LD + i];
+        if constexpr (CPLX) {
+          const double2 ph = rot_ph[k];
+          const double2 xqe = cmul(xq, ph);
+          X[p * LD + i] = make_double2(c * xp.x - s * xqe.x, c * xp.y - s * xqe.y);
+          X[q * LD + i] = make_double2(s * xp.x + c * xqe.x, s * xp.y + c * xqe.y);
+        } else {
+          const double xqe = xq * rot_ph[k].x;
+          X[p * LD + i] = c * xp - s * xqe;
+          X[q * LD + i] = s * xp + c * xqe;
+        }
+      }
+      __syncthreads();
+      // row phase (S only): S(p,:) <- c S(p,:) - s e^{+i th} S(q,:) ; S(q,:) <- s S(p,:) + c e^{+i th} S(q,:)
+      for (int e = tid; e < H * N; e += nt) {
+        const int j = e % N;
+        const int k = e / N;
+        int p = (k == 0) ? (N - 1) : (round + k) % (N - 1);
+        int q = (round + (N - 1) - k) % (N - 1);
+        if (p > q) { int t = p; p = q; q = t; }
+        const double c = rot_c[k], s = rot_s[k];
+        if (s == 0.0) continue;
+        const T xp = S[j * LD + p], xq = S[j * LD + q];
+        if constexpr (CPLX) {
+          const double2 ph = rot_ph[k];
+          const double2 xqe = cmulc(ph, xq);   // e^{+i th} * xq
+          S[j * LD + p] = make_double2(c * xp.x - s * xqe.x, c * xp.y - s * xqe.y);
+          S[j * LD + q] = make_double2(s * xp.x + c * xqe.x, s * xp.y + c * xqe.y);
+        } else {
+          const double xqe = xq * rot_ph[k].x;
+          S[j * LD + p] = c * xp - s * xqe;
+          S[j * LD + q] = s * xp + c * xqe;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < N * N; e += nt) {
+    const int i = e % N, j = e / N;
+    Wout[e] = W[j * LD + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// helper kernels
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void set_identity_kernel(T* V, long long rows, long long cols) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e % rows, j = e / rows;
+    if constexpr (sizeof(T) == 16) V[e] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    else V[e] = (i == j) ? 1.0 : 0.0;
+  }
+}
+
+// one block per column: nrm[j] = ||G(:,j)||; if V != null also sgn[j] = Re(V(:,j)^H G(:,j)) (eigh sign)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) colnorm_kernel(const typename JT<CPLX>::T* __restrict__ G, long long ldg, long long m,
+                                                      const typename JT<CPLX>::T* __restrict__ V, long long ldv,
+                                                      double* nrm, double* sgn, double* vn2) {
+  using T = typename JT<CPLX>::T;
+  const T* g = G + (size_t)blockIdx.x * ldg;
+  const T* v = V ? V + (size_t)blockIdx.x * ldv : nullptr;
+  double s = 0, d = 0, w = 0;
+  for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+    const T x = g[i];
+    if constexpr (CPLX) { s += x.x * x.x + x.y * x.y; if (v) { const T y = v[i]; d += y.x * x.x + y.y * x.y; w += y.x * y.x + y.y * y.y; } }
+    else { s += x * x; if (v) { d += v[i] * x; w += v[i] * v[i]; } }
+  }
+  __shared__ double r1[8], r2[8], r3[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o); d += __shfl_xor_sync(0xffffffffu, d, o); w += __shfl_xor_sync(0xffffffffu, w, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s; r2[threadIdx.x >> 5] = d; r3[threadIdx.x >> 5] = w; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int i = 0; i < 8; ++i) { a += r1[i]; b += r2[i]; c += r3[i]; }
+    nrm[blockIdx.x] = sqrt(a);
+    if (sgn) sgn[blockIdx.x] = b;
+    if (vn2) vn2[blockIdx.x] = c;
+  }
+}
+
+// out(:,k) = scale_k * src(:,perm[k])  (optionally conjugated); scale_k = inv ? 1/s[perm[k]] : 1
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gather_cols_kernel(typename JT<CPLX>::T* out, long long ldo,
+                                                          const typename JT<CPLX>::T* __restrict__ src, long long lds,
+                                                          long long rows, const int* __restrict__ perm,
+                                                          const double* __restrict__ s, int inv, int conj) {
+  using T = typename JT<CPLX>::T;
+  const int k = blockIdx.y;
+  const int j = perm[k];
+  double f = 1.0;
+  if (inv) { const double sv = s[j]; f = sv > 0.0 ? 1.0 / sv : 0.0; }
+  const T* sp = src + (size_t)j * lds;
+  T* op = out + (size_t)k * ldo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    T x = sp[i];
+    if constexpr (CPLX) { x.x *= f; x.y *= (conj ? -f : f); } else x *= f;
+    op[i] = x;
+  }
+}
+
+// make a Hermitian matrix full from its upper triangle (syevd 'U' semantics)
+template <bool CPLX>
+__global__ void symmetrize_upper_kernel(typename JT<CPLX>::T* A, long long n) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e % n, j = e / n;
+    if (i > j) {
+      auto v = A[j + i * n];
+      if constexpr (CPLX) v.y = -v.y;
+      A[e] = v;
+    } else if (i == j) {
+      if constexpr (CPLX) A[e].y = 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// driver
+// ------------------------------------------------------------------------------------
+struct JacobiOut {
+  void* G;        // m x npad, converged (orthogonal columns)
+  void* V;        // n x npad accumulated rotations (A V = G), or null
+  long long ldg, ldv;
+  int npad;
+};
+
+size_t jacobi_ws_bytes(int dtype, int64_t m, int64_t n, bool want_v) {
+  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
+  const int b = NB2 / 2;
+  int64_t nblk = (n + b - 1) / b;
+  if (nblk & 1) ++nblk;
+  if (nblk < 2) nblk = 2;
+  const int64_t npad = nblk * b;
+  const size_t es = elsize(dtype);
+  size_t tot = 2 * al256((size_t)m * npad * es);
+  if (want_v) tot += 2 * al256((size_t)n * npad * es);
+  tot += 2 * al256((size_t)(nblk / 2) * NB2 * NB2 * es);   // S and W batches
+  tot += 4 * al256((size_t)nblk * sizeof(long long));      // offset tables
+  tot += al256(64);
+  return tot + 4096;
+}
+
+// Runs the sweeps.  A (m x n, column-major, lda) is copied in; result buffers live in the arena.
+template <bool CPLX>
+static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda, bool want_v, JacobiOut* out,
+                      int* sweeps_done, cudaStream_t st) {
+  using T = typename JT<CPLX>::T;
+  constexpr int NB2 = JT<CPLX>::NB2;
+  constexpr int b = NB2 / 2;
+  const int dtype = CPLX ? TNB_C128 : TNB_F64;
+  int64_t nblk = (n + b - 1) / b;
+  if (nblk & 1) ++nblk;
+  if (nblk < 2) nblk = 2;
+  const int64_t npad = nblk * b;
+  const int k = (int)(nblk / 2);
+  const size_t es = sizeof(T);
+  void *G0, *G1, *V0 = nullptr, *V1 = nullptr, *Sb, *Wb, *tA, *tB, *tCg, *tCv, *dscal;
+  TNB_TRY(ws_alloc(h, (size_t)m * npad * es, &G0));
+  TNB_TRY(ws_alloc(h, (size_t)m * npad * es, &G1));
+  if (want_v) {
+    TNB_TRY(ws_alloc(h, (size_t)n * npad * es, &V0));
+    TNB_TRY(ws_alloc(h, (size_t)n * npad * es, &V1));
+  }
+  TNB_TRY(ws_alloc(h, (size_t)k * NB2 * NB2 * es, &Sb));
+  TNB_TRY(ws_alloc(h, (size_t)k * NB2 * NB2 * es, &Wb));
+  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tA));
+  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tB));
+  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tCg));
+  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tCv));
+  TNB_TRY(ws_alloc(h, 64, &dscal));
+  // G0 = [A 0]
+  TNB_CUDA(h, cudaMemsetAsync(G0, 0, (size_t)m * npad * es, st));
+  TNB_CUDA(h, cudaMemcpy2DAsync(G0, (size_t)m * es, A, (size_t)lda * es, (size_t)m * es, (size_t)n, cudaMemcpyDeviceToDevice, st));
+  if (want_v) {
+    set_identity_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)V0, n, npad);
+    h->launches++;
+  }
+  // offset tables for the rotate GEMMs: batch q = (pair p, half hf).  Destination slot of each
+  // half follows the round-robin rotation with slot 0 fixed (top row T_i = slot 2i, bottom B_i = 2i+1):
+  //   T_0 -> T_0 ; B_0 -> T_1 ; T_i -> T_{i+1} (1<=i<=k-2) ; T_{k-1} -> B_{k-1} ; B_i -> B_{i-1} (i>=1)
+  std::vector<long long> oa(nblk), ob(nblk), ocg(nblk), ocv(nblk);
+  for (int p = 0; p < k; ++p)
+    for (int hf = 0; hf < 2; ++hf) {
+      const int q = 2 * p + hf;
+      int dst;
+      if (k == 1) dst = q;
+      else if (hf == 0) dst = (p == 0) ? 0 : (p == k - 1 ? 2 * (k - 1) + 1 : 2 * (p + 1));
+      else dst = (p == 0) ? 2 : 2 * (p - 1) + 1;
+      oa[q] = (long long)p * NB2;               // in columns; scaled by ld below
+      ob[q] = (long long)p * NB2 * NB2 + (long long)hf * b * NB2;
+      ocg[q] = (long long)dst * b * m;
+      ocv[q] = (long long)dst * b * n;
+    }
+  std::vector<long long> oag(nblk), oav(nblk);
+  for (int q = 0; q < (int)nblk; ++q) { oag[q] = oa[q] * m; oav[q] = oa[q] * n; }
+  // tA holds G-side A offsets; V-side A offsets reuse tCv's buffer layout? keep separate small uploads
+  void* tAv;
+  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tAv));
+  TNB_CUDA(h, cudaMemcpyAsync(tA, oag.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(tAv, oav.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(tB, ob.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(tCg, ocg.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(tCv, ocv.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaStreamSynchronize(st));   // host vectors go out of scope below
+
+  auto eig = small_eigh_kernel<CPLX, NB2>;
+  constexpr int SMEM = 2 * NB2 * (NB2 + 1) * (int)sizeof(T);
+  static bool attr = false;
+  if (!attr) { TNB_CUDA(h, cudaFuncSetAttribute(eig, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+
+  const double tol = std::max(1e-14, std::sqrt((double)m) * 2.3e-16);
+  const int steps = (k == 1) ? 1 : (int)nblk - 1;
+  int cur = 0;
+  void* Gs[2] = {G0, G1};
+  void* Vs[2] = {V0, V1};
+  int sweep = 0;
+  const int max_sweeps = 40;
+  for (; sweep < max_sweeps; ++sweep) {
+    TNB_CUDA(h, cudaMemsetAsync(dscal, 0, 8, st));
+    for (int s = 0; s < steps; ++s) {
+      // 1. Gram of every pair
+      TNB_TRY(gemm_batched_impl(h, dtype, 'C', 'N', NB2, NB2, m, nullptr, Gs[cur], m, nullptr, (long long)NB2 * m,
+                                Gs[cur], m, nullptr, (long long)NB2 * m, nullptr, Sb, NB2, nullptr,
+                                (long long)NB2 * NB2, k, st));
+      // 2. diagonalise
+      eig<<<k, 1024, SMEM, st>>>((const T*)Sb, (T*)Wb, (double*)dscal, 30);
+      h->launches++;
+      // 3. rotate G and V into next-step slots
+      TNB_TRY(gemm_batched_impl(h, dtype, 'N', 'N', m, b, NB2, nullptr, Gs[cur], m, (const long long*)tA, 0, Wb, NB2,
+                                (const long long*)tB, 0, nullptr, Gs[cur ^ 1], m, (const long long*)tCg, 0, (int)nblk, st));
+      if (want_v)
+        TNB_TRY(gemm_batched_impl(h, dtype, 'N', 'N', n, b, NB2, nullptr, Vs[cur], n, (const long long*)tAv, 0, Wb, NB2,
+                                  (const long long*)tB, 0, nullptr, Vs[cur ^ 1], n, (const long long*)tCv, 0, (int)nblk, st));
+      cur ^= 1;
+    }
+    TNB_CUDA(h, cudaGetLastError());
+    TNB_CUDA(h, cudaMemcpyAsync(h->scal_host + 100, dscal, 8, cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(h, cudaStreamSynchronize(st));
+    if (h->scal_host[100] < tol) { ++sweep; break; }
+  }
+  if (sweeps_done) *sweeps_done = sweep;
+  if (sweep >= max_sweeps && !(h->scal_host[100] < tol * 100))
+    return set_err(h, TNB_ERR_NO_CONVERGENCE, "jacobi: no convergence after %d sweeps (off = %.3e)", sweep, h->scal_host[100]);
+  out->G = Gs[cur]; out->V = want_v ? Vs[cur] : nullptr; out->ldg = m; out->ldv = n; out->npad = (int)npad;
+  return TNB_OK;
+}
+
+// Sort descending by key on the host, upload the permutation.  keys_dev has npad entries.
+static int sort_desc(Handle* h, const double* keys_dev, int npad, int* perm_dev, double* sorted_dev, std::vector<double>& keys,
+                     std::vector<int>& perm, cudaStream_t st) {
+  keys.resize(npad);
+  TNB_CUDA(h, cudaMemcpyAsync(keys.data(), keys_dev, npad * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(h, cudaStreamSynchronize(st));
+  perm.resize(npad);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return keys[a] > keys[b]; });
+  std::vector<double> sorted(npad);
+  for (int i = 0; i < npad; ++i) sorted[i] = keys[perm[i]];
+  TNB_CUDA(h, cudaMemcpyAsync(perm_dev, perm.data(), npad * sizeof(int), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(sorted_dev, sorted.data(), npad * sizeof(double), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaStreamSynchronize(st));
+  keys = sorted;
+  return TNB_OK;
+}
+
+// Thin SVD of A (m x n): U (m x kmax), S (kmax), V (n x kmax) with A ~ U diag(S) V^T.
+// Works on the taller orientation internally.  Arena must have been sized by the caller
+// (svd_ws_bytes).  If P_out != null it receives S^2 (kmax entries, device).
+template <bool CPLX>
+static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda, int64_t kmax, int64_t ks, void* U,
+                    int64_t ldu, double* S, void* V, int64_t ldv, cudaStream_t st) {
+  using T = typename JT<CPLX>::T;
+  const int dtype = CPLX ? TNB_C128 : TNB_F64;
+  const bool transposed = m < n;
+  const void* Awork = A;
+  int64_t mm = m, nn = n, ld = lda;
+  void* At = nullptr;
+  if (transposed) {
+    // work on A^H (n x m): explicit conjugate transpose through the permute kernel
+    TNB_TRY(ws_alloc(h, (size_t)m * n * sizeof(T), &At));
+    if (lda != m) return set_err(h, TNB_ERR_UNSUPPORTED, "svd: lda != m with m < n");
+    int64_t ext[2] = {m, n};
+    int32_t ma[2] = {0, 1}, mb[2] = {1, 0};
+    TNB_TRY(permute_axpby_impl(h, dtype, 2, ext, ma, A, mb, At, nullptr, nullptr, st));
+    Awork = At; mm = n; nn = m; ld = n;
+  }
+  JacobiOut jo;
+  int sweeps = 0;
+  TNB_TRY(jacobi_run<CPLX>(h, mm, nn, Awork, ld, true, &jo, &sweeps, st));
+  void *nrm, *perm, *sorted;
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &nrm));
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(int), &perm));
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &sorted));
+  colnorm_kernel<CPLX><<<jo.npad, 256, 0, st>>>((const T*)jo.G, jo.ldg, mm, nullptr, 0, (double*)nrm, nullptr, nullptr);
+  h->launches++;
+  std::vector<double> keys;
+  std::vector<int> pv;
+  TNB_TRY(sort_desc(h, (const double*)nrm, jo.npad, (int*)perm, (double*)sorted, keys, pv, st));
+  TNB_CUDA(h, cudaMemcpyAsync(S, sorted, ks * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  // left factor of the worked matrix = normalised G columns; right factor = V columns.
+  // A = Uw S Vw^H.  Not transposed: U = Uw, Vout = conj(Vw).  Transposed (worked on A^H = Uw S Vw^H
+  // => A = Vw S Uw^H): U = Vw, Vout = conj(Uw).
+  // With A = U S Vout^T we need Vout = conj(right singular vectors).
+  dim3 gU((unsigned)std::min<int64_t>((mm + 255) / 256, 64), (unsigned)kmax);
+  dim3 gV((unsigned)std::min<int64_t>((nn + 255) / 256, 64), (unsigned)kmax);
+  if (!transposed) {
+    gather_cols_kernel<CPLX><<<gU, 256, 0, st>>>((T*)U, ldu, (const T*)jo.G, jo.ldg, mm, (const int*)perm, (const double*)nrm, 1, 0);
+    gather_cols_kernel<CPLX><<<gV, 256, 0, st>>>((T*)V, ldv, (const T*)jo.V, jo.ldv, nn, (const int*)perm, nullptr, 0, 1);
+  } else {
+    gather_cols_kernel<CPLX><<<gV, 256, 0, st>>>((T*)U, ldu, (const T*)jo.V, jo.ldv, nn, (const int*)perm, nullptr, 0, 0);
+    gather_cols_kernel<CPLX><<<gU, 256, 0, st>>>((T*)V, ldv, (const T*)jo.G, jo.ldg, mm, (const int*)perm, (const double*)nrm, 1, 1);
+  }
+  h->launches += 2;
+  return check_cuda(h, cudaGetLastError(), "svd gather");
+}
+
+size_t svd_ws_bytes(int dtype, int64_t m, int64_t n) {
+  const int64_t mm = std::max(m, n), nn = std::min(m, n);
+  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
+  const int64_t npad = ((nn + NB2 / 2 - 1) / (NB2 / 2) + 2) * (NB2 / 2);
+  return jacobi_ws_bytes(dtype, mm, nn, true) + al256((size_t)m * n * elsize(dtype)) + 3 * al256(npad * 8) + 4096;
+}
+
+int svd_impl(Handle* h, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, int64_t kmax, int64_t ks, void* U,
+             int64_t ldu, double* S, void* V, int64_t ldv, cudaStream_t st) {
+  if (dtype == TNB_F64) return svd_core<false>(h, m, n, A, lda, kmax, ks, U, ldu, S, V, ldv, st);
+  if (dtype == TNB_C128) return svd_core<true>(h, m, n, A, lda, kmax, ks, U, ldu, S, V, ldv, st);
+  return set_err(h, TNB_ERR_UNSUPPORTED, "svd: dtype %d", dtype);
+}
+
+// Hermitian eigendecomposition via one-sided Jacobi on A itself: A V = G = V Lambda.
+// |lambda_j| = ||g_j||, sign from Re(v_j^H g_j).  Eigenvalues sorted DEscending.  D (kmax), U (n x kmax).
+// A positive semi-definite input (the DMRG density matrix) keeps high relative accuracy.
+template <bool CPLX>
+static int eigh_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu, cudaStream_t st) {
+  using T = typename JT<CPLX>::T;
+  symmetrize_upper_kernel<CPLX><<<h->num_sms * 4, 256, 0, st>>>((T*)A, n);
+  h->launches++;
+  JacobiOut jo;
+  int sweeps = 0;
+  TNB_TRY(jacobi_run<CPLX>(h, n, n, A, n, true, &jo, &sweeps, st));
+  void *nrm, *sgn, *perm, *sorted, *vn2;
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &nrm));
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &sgn));
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &vn2));
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(int), &perm));
+  TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &sorted));
+  // padded columns of V are not n rows long in G's sense; V is n x npad with ldv = n: fine
+  colnorm_kernel<CPLX><<<jo.npad, 256, 0, st>>>((const T*)jo.G, jo.ldg, n, (const T*)jo.V, jo.ldv, (double*)nrm, (double*)sgn, (double*)vn2);
+  h->launches++;
+  // eigenvalue = sign(sgn) * nrm, computed on the host during the sort
+  std::vector<double> hn(jo.npad), hs(jo.npad), hv(jo.npad);
+  TNB_CUDA(h, cudaMemcpyAsync(hn.data(), nrm, jo.npad * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(h, cudaMemcpyAsync(hs.data(), sgn, jo.npad * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(h, cudaMemcpyAsync(hv.data(), vn2, jo.npad * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TNB_CUDA(h, cudaStreamSynchronize(st));
+  std::vector<double> lam(jo.npad);
+  for (int j = 0; j < jo.npad; ++j) lam[j] = (j < jo.npad && hs[j] < 0.0) ? -hn[j] : hn[j];
+  // padded columns must sort after genuine ones, including genuine negative eigenvalues
+  std::vector<int> pv(jo.npad);
+  std::iota(pv.begin(), pv.end(), 0);
+  std::vector<char> is_pad(jo.npad, 0);
+  // a padding column's V column is a unit vector supported on rows >= n, i.e. zero in the n stored rows
+  for (int j = 0; j < jo.npad; ++j) is_pad[j] = (hv[j] < 0.5) ? 1 : 0;
+  std::stable_sort(pv.begin(), pv.end(), [&](int a, int b) {
+    if (is_pad[a] != is_pad[b]) return is_pad[a] < is_pad[b];
+    return lam[a] > lam[b];
+  });
+  std::vector<double> sorted_h(jo.npad);
+  for (int i = 0; i < jo.npad; ++i) sorted_h[i] = lam[pv[i]];
+  TNB_CUDA(h, cudaMemcpyAsync(perm, pv.data(), jo.npad * sizeof(int), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(sorted, sorted_h.data(), jo.npad * sizeof(double), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaStreamSynchronize(st));
+  TNB_CUDA(h, cudaMemcpyAsync(D, sorted, ks * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  dim3 gV((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)kmax);
+  gather_cols_kernel<CPLX><<<gV, 256, 0, st>>>((T*)U, ldu, (const T*)jo.V, jo.ldv, n, (const int*)perm, nullptr, 0, 0);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "eigh gather");
+}
+
+size_t eigh_ws_bytes(int dtype, int64_t n) {
+  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
+  const int64_t npad = ((n + NB2 / 2 - 1) / (NB2 / 2) + 2) * (NB2 / 2);
+  return jacobi_ws_bytes(dtype, n, n, true) + 5 * al256(npad * 8) + 4096;
+}
+
+int eigh_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu, cudaStream_t st) {
+  if (dtype == TNB_F64) return eigh_core<false>(h, n, A, kmax, ks, D, U, ldu, st);
+  if (dtype == TNB_C128) return eigh_core<true>(h, n, A, kmax, ks, D, U, ldu, st);
+  return set_err(h, TNB_ERR_UNSUPPORTED, "eigh: dtype %d", dtype);
+}
+
+}  // namespace tnb

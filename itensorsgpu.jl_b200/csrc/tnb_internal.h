@@ -31,6 +31,12 @@ struct GemmParams {
   double alpha_re, alpha_im, beta_re, beta_im;
   int conjA, conjB;
   int tilesM, tilesN, groupM;
+  // batched form: blockIdx.y = batch; element offsets added to A/B/C (device arrays or strides)
+  int batch;
+  const long long* boffA;
+  const long long* boffB;
+  const long long* boffC;
+  long long bstrideA, bstrideB, bstrideC;   // used when the corresponding boff* is null
 };
 
 struct Handle {
@@ -40,6 +46,7 @@ struct Handle {
   char* ws = nullptr;       // workspace arena
   size_t ws_bytes = 0;
   size_t ws_off = 0;        // bump pointer (reset by each public entry point)
+  size_t ws_base = 0;       // bytes at the front of the arena pinned by an outer entry point
   double* scal = nullptr;   // small device scalar pool (256 doubles)
   double* scal_host = nullptr;  // pinned mirror
   uint64_t launches = 0;
@@ -56,7 +63,7 @@ int ws_alloc(Handle* h, size_t bytes, void** out);
 // Ensure the arena holds at least `bytes` BEFORE a sequence of ws_alloc calls, so that
 // pointers handed out earlier in the same entry point stay valid.
 int ws_require(Handle* h, size_t bytes);
-inline void ws_reset(Handle* h) { h->ws_off = 0; }
+inline void ws_reset(Handle* h) { h->ws_off = h->ws_base; }
 
 #define TNB_CUDA(h, call)                                   \
   do {                                                      \
@@ -79,6 +86,14 @@ int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32
 int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
               const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
               const void* beta, void* C, int64_t ldc, cudaStream_t st);
+
+// batched column-major GEMM: for b in [0,batch): C_b = alpha*op(A_b)*op(B_b) + beta*C_b where
+// X_b = X + (offX ? offX[b] : b*strideX) elements.  offX are DEVICE arrays.
+int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
+                      const void* alpha, const void* A, int64_t lda, const long long* offA, long long strideA,
+                      const void* B, int64_t ldb, const long long* offB, long long strideB, const void* beta,
+                      void* C, int64_t ldc, const long long* offC, long long strideC, int batch,
+                      cudaStream_t st);
 
 // ---- vector ops (vecops.cu)
 int permute_axpby_impl(Handle* h, int dtype, int n, const int64_t* extA, const int32_t* modeA,
@@ -109,6 +124,22 @@ int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, co
 int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
                     const void* W2, const void* R, const void* phi, int ortho, double noise,
                     int accumulate, void* rho, void* t0, void* t1, cudaStream_t st);
+
+// y <- x / *scal (0 if *scal <= tol); x and y may alias (vecops.cu)
+int scale_inv_dev_impl(Handle* h, int dtype, int64_t n, const void* x, void* y, const double* scal, double tol,
+                       cudaStream_t st);
+
+// ---- factorizations (jacobi.cu, qr.cu)
+size_t svd_ws_bytes(int dtype, int64_t m, int64_t n);
+size_t eigh_ws_bytes(int dtype, int64_t n);
+size_t qr_ws_bytes(int dtype, int64_t m, int64_t n);
+// U: m x kmax, V: n x kmax (A ~ U diag(S) V^T); S receives the first ks singular values (ks <= min(m,n))
+int svd_impl(Handle* h, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, int64_t kmax, int64_t ks,
+             void* U, int64_t ldu, double* S, void* V, int64_t ldv, cudaStream_t st);
+// eigenvalues descending; D receives the first ks, U (n x kmax) the first kmax eigenvectors; A destroyed
+int eigh_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu,
+              cudaStream_t st);
+int qr_impl(Handle* h, int dtype, int64_t m, int64_t n, const void* A, void* Q, void* R, cudaStream_t st);
 
 inline size_t elsize(int dtype) { return dtype == TNB_C128 ? 16 : 8; }
 

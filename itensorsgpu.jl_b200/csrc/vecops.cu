@@ -335,6 +335,24 @@ int nrm2_impl(Handle* h, int dtype, int64_t n, const void* x, double* result_dev
   return reduce_launch(h, 2, x, nullptr, dtype == TNB_C128 ? 2 * n : n, result_dev, st);
 }
 
+__global__ void __launch_bounds__(256) scale_inv_generic_kernel(double* y, const double* x, long long nd,
+                                                               const double* scal, double tol) {
+  const double b = scal[0];
+  const double f = b > tol ? 1.0 / b : 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * f;
+}
+
+int scale_inv_dev_impl(Handle* h, int dtype, int64_t n, const void* x, void* y, const double* scal, double tol,
+                       cudaStream_t st) {
+  const long long nd = dtype == TNB_C128 ? 2 * n : n;
+  if (nd <= 0) return TNB_OK;
+  const int grid = grid_for(h, nd, 256 * 4);
+  scale_inv_generic_kernel<<<grid, 256, 0, st>>>((double*)y, (const double*)x, nd, scal, tol);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "scale_inv launch");
+}
+
 // ------------------------------------------------------------------------------------
 // spectrum truncation -- CPU rule of [EXT] NDTensors truncate!, one kernel, one readback.
 // out[0] = truncerr, out[1] = docut, out[2] = n_keep.

@@ -304,3 +304,150 @@ def noise_term(L, W1, W2, R, phi, ortho, noise, rho=None):
                                  _ptr(R.data), _ptr(phi.data), 0 if ortho == "left" else 1, float(noise), acc,
                                  _ptr(rho.data), _stream()))
     return rho
+
+
+# ------------------------------------------------------------------ factorizations
+def _matrix_dims(M):
+    if len(M.dims) != 2:
+        raise _lib.TnbError(1, "rank-2 tensor expected, got dims %s" % (M.dims,))
+    return M.dims
+
+
+def svd(M, maxdim=None, mindim=1, cutoff=None, use_absolute_cutoff=False, use_relative_cutoff=True):
+    """Thin SVD + truncation.  Returns (U[m,k], S[k] (torch), V[n,k], truncerr) with M ~ U diag(S) V^T
+    (``svd``: reference ``src/tensor/culinearalgebra.jl:33-72``; CPU ``conj!(MV)`` convention)."""
+    h = _lib.handle()
+    m, n = _matrix_dims(M)
+    do_trunc = maxdim is not None or cutoff is not None
+    kfull = min(m, n)
+    kmax = min(kfull, int(maxdim)) if (do_trunc and maxdim is not None) else kfull
+    A = M.clone()
+    U = DTensor.empty((m, kmax), M.dtype, M.data.device)
+    V = DTensor.empty((n, kmax), M.dtype, M.data.device)
+    S = torch.empty(kmax, dtype=torch.float64, device=M.data.device)
+    nk = C.c_int64(0)
+    err = C.c_double(0.0)
+    flags = (1 if use_absolute_cutoff else 0) | (0 if use_relative_cutoff else 2)
+    h.check(h.lib.tnb_svd_trunc(h.h, _dt(M.data), m, n, _ptr(A.data), int(maxdim) if maxdim is not None else 0,
+                                int(mindim), float(cutoff or 0.0), flags, 1 if do_trunc else 0, _ptr(U.data), _ptr(S),
+                                _ptr(V.data), C.byref(nk), C.byref(err), _stream()))
+    k = nk.value
+    return (DTensor(U.data[: m * k], (m, k)), S[:k], DTensor(V.data[: n * k], (n, k)), err.value)
+
+
+def eigh(M, maxdim=None, mindim=1, cutoff=None, use_absolute_cutoff=False, use_relative_cutoff=True):
+    """Hermitian eigendecomposition, eigenvalues descending + truncation.  Returns (D[k] torch, U[n,k], truncerr)
+    (``eigen``: reference ``src/tensor/culinearalgebra.jl:74-108``)."""
+    h = _lib.handle()
+    n, n2 = _matrix_dims(M)
+    if n != n2:
+        raise _lib.DimensionMismatch(2, "eigh: matrix is %dx%d" % (n, n2))
+    do_trunc = maxdim is not None or cutoff is not None
+    kmax = min(n, int(maxdim)) if (do_trunc and maxdim is not None) else n
+    A = M.clone()
+    U = DTensor.empty((n, kmax), M.dtype, M.data.device)
+    D = torch.empty(kmax, dtype=torch.float64, device=M.data.device)
+    nk = C.c_int64(0)
+    err = C.c_double(0.0)
+    flags = (1 if use_absolute_cutoff else 0) | (0 if use_relative_cutoff else 2)
+    h.check(h.lib.tnb_eigh_trunc(h.h, _dt(M.data), n, _ptr(A.data), int(maxdim) if maxdim is not None else 0,
+                                 int(mindim), float(cutoff or 0.0), flags, 1 if do_trunc else 0, _ptr(D), _ptr(U.data),
+                                 C.byref(nk), C.byref(err), _stream()))
+    k = nk.value
+    return D[:k], DTensor(U.data[: n * k], (n, k)), err.value
+
+
+def qr(M):
+    """Thin QR, explicit Q, diag(R) >= 0 (``qr``: reference ``src/tensor/culinearalgebra.jl:110-121``)."""
+    h = _lib.handle()
+    m, n = _matrix_dims(M)
+    k = min(m, n)
+    Q = DTensor.empty((m, k), M.dtype, M.data.device)
+    R = DTensor.empty((k, n), M.dtype, M.data.device)
+    h.check(h.lib.tnb_qr(h.h, _dt(M.data), m, n, _ptr(M.data), _ptr(Q.data), _ptr(R.data), _stream()))
+    return Q, R
+
+
+_DECOMP = {None: 0, "automatic": 0, "svd": 1, "eigen": 2, "qr": 3}
+
+
+def factorize_bond(phi, ortho="left", which_decomp=None, maxdim=None, mindim=1, cutoff=0.0, rho_pert=None,
+                   normalize=False):
+    """phi[l,s1,s2,r] -> A[l,s1,k], B[k,s2,r]  ([EXT] replacebond!/factorize).  Returns (A, B, truncerr)."""
+    h = _lib.handle()
+    cl, d1, d2, cr = phi.dims
+    m, n = cl * d1, d2 * cr
+    if which_decomp == "eigen" or (which_decomp is None and (rho_pert is not None or (cutoff or 0.0) > 1e-12)):
+        rfull = m if ortho == "left" else n
+    else:
+        rfull = min(m, n)
+    kmax = min(rfull, int(maxdim)) if maxdim is not None else rfull
+    kmax = max(kmax, 1)
+    bd = BondDims(cl, cr, d1, d2, 1, 1, 1)
+    work = phi.clone()
+    A = DTensor.empty((m * kmax,), phi.dtype, phi.data.device)
+    B = DTensor.empty((kmax * n,), phi.dtype, phi.data.device)
+    nk = C.c_int64(0)
+    err = C.c_double(0.0)
+    h.check(h.lib.tnb_factorize_bond(h.h, _dt(phi.data), C.byref(bd), _ptr(work.data), 0 if ortho == "left" else 1,
+                                     _DECOMP[which_decomp], int(maxdim) if maxdim is not None else 0, int(mindim),
+                                     float(cutoff or 0.0), _ptr(rho_pert.data) if rho_pert is not None else None,
+                                     1 if normalize else 0, _ptr(A.data), _ptr(B.data), C.byref(nk), C.byref(err),
+                                     _stream()))
+    k = nk.value
+    return DTensor(A.data[: m * k], (cl, d1, k)), DTensor(B.data[: k * n], (k, d2, cr)), err.value
+
+
+def dmrg_bond_step(L, W1, W2, R, A1, A2, ortho, maxdim, mindim=1, cutoff=0.0, noise=0.0, krylovdim=3, maxiter=1,
+                   which_decomp=None):
+    """One two-site DMRG bond update through the single fused C call.  Returns (energy, A1', A2', truncerr)."""
+    h = _lib.handle()
+    cl, d1, cm = A1.dims
+    cm2, d2, cr = A2.dims
+    if cm != cm2:
+        raise _lib.DimensionMismatch(2, "A1/A2 middle bond differs")
+    m, n = cl * d1, d2 * cr
+    use_eigen = which_decomp == "eigen" or (which_decomp is None and (noise > 0 or (cutoff or 0.0) > 1e-12))
+    rfull = (m if ortho == "left" else n) if use_eigen else min(m, n)
+    kmax = max(1, min(rfull, int(maxdim)))
+    bd = BondDims(cl, cr, d1, d2, W1.dims[0], W1.dims[3], W2.dims[3])
+    dev = A1.data.device
+    b1 = torch.empty(max(A1.size, m * kmax), dtype=A1.dtype, device=dev)
+    b2 = torch.empty(max(A2.size, kmax * n), dtype=A2.dtype, device=dev)
+    b1[: A1.size].copy_(A1.data)
+    b2[: A2.size].copy_(A2.data)
+    e = C.c_double(0.0)
+    nk = C.c_int64(0)
+    err = C.c_double(0.0)
+    h.check(h.lib.tnb_dmrg_bond_step(h.h, _dt(A1.data), C.byref(bd), cm, _ptr(L.data), _ptr(W1.data), _ptr(W2.data),
+                                     _ptr(R.data), _ptr(b1), _ptr(b2), 0 if ortho == "left" else 1,
+                                     _DECOMP[which_decomp], int(maxdim), int(mindim), float(cutoff or 0.0),
+                                     float(noise), int(krylovdim), int(maxiter), C.byref(e), C.byref(nk),
+                                     C.byref(err), _stream()))
+    k = nk.value
+    return e.value, DTensor(b1[: m * k], (cl, d1, k)), DTensor(b2[: k * n], (k, d2, cr)), err.value
+
+
+def tebd_apply_gate(G, A1, A2, maxdim=None, mindim=1, cutoff=0.0):
+    """theta = G * (A1*A2), left-orthogonal split ([EXT] apply / product(o, psi)).  Returns (A1', A2', truncerr)."""
+    h = _lib.handle()
+    cl, d1, cm = A1.dims
+    _, d2, cr = A2.dims
+    m, n = cl * d1, d2 * cr
+    G, A1 = _promote(G, A1)
+    G, A2 = _promote(G, A2)
+    use_eigen = (cutoff or 0.0) > 1e-12
+    rfull = m if use_eigen else min(m, n)
+    kmax = max(1, min(rfull, int(maxdim)) if maxdim is not None else rfull)
+    dev = A1.data.device
+    b1 = torch.empty(max(A1.size, m * kmax), dtype=A1.dtype, device=dev)
+    b2 = torch.empty(max(A2.size, kmax * n), dtype=A2.dtype, device=dev)
+    b1[: A1.size].copy_(A1.data)
+    b2[: A2.size].copy_(A2.data)
+    nk = C.c_int64(0)
+    err = C.c_double(0.0)
+    h.check(h.lib.tnb_tebd_apply_gate(h.h, _dt(A1.data), cl, cm, cr, d1, d2, _ptr(G.data), _ptr(b1), _ptr(b2),
+                                      int(maxdim) if maxdim is not None else 0, int(mindim), float(cutoff or 0.0),
+                                      C.byref(nk), C.byref(err), _stream()))
+    k = nk.value
+    return DTensor(b1[: m * k], (cl, d1, k)), DTensor(b2[: k * n], (k, d2, cr)), err.value
