@@ -161,9 +161,36 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
       __syncthreads();
     }
   }
+  // Newton-Schulz polish: a few hundred plane rotations per column leave W orthogonal only to
+  // ~1e-14; one step W <- W (I - E/2), E = W^H W - I, restores it to rounding level (E^2 ~ 1e-27),
+  // so the accumulated V = prod W stays orthonormal over thousands of products.  S is dead here
+  // and is reused for E.
+  __syncthreads();
   for (int e = tid; e < N * N; e += nt) {
     const int i = e % N, j = e / N;
-    Wout[e] = W[j * LD + i];
+    if constexpr (CPLX) {
+      double2 acc = make_double2(i == j ? -1.0 : 0.0, 0.0);
+      for (int k = 0; k < N; ++k) { const double2 t = cmulc(W[i * LD + k], W[j * LD + k]); acc.x += t.x; acc.y += t.y; }
+      S[j * LD + i] = acc;
+    } else {
+      double acc = (i == j) ? -1.0 : 0.0;
+      for (int k = 0; k < N; ++k) acc += W[i * LD + k] * W[j * LD + k];
+      S[j * LD + i] = acc;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < N * N; e += nt) {
+    const int i = e % N, j = e / N;
+    if constexpr (CPLX) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int k = 0; k < N; ++k) { const double2 t = cmul(W[k * LD + i], S[j * LD + k]); acc.x += t.x; acc.y += t.y; }
+      const double2 w = W[j * LD + i];
+      Wout[e] = make_double2(w.x - 0.5 * acc.x, w.y - 0.5 * acc.y);
+    } else {
+      double acc = 0.0;
+      for (int k = 0; k < N; ++k) acc += W[k * LD + i] * S[j * LD + k];
+      Wout[e] = W[j * LD + i] - 0.5 * acc;
+    }
   }
 }
 
@@ -406,7 +433,7 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
   int64_t mm = m, nn = n, ld = lda;
   void* At = nullptr;
   if (transposed) {
-    // work on A^H (n x m): explicit conjugate transpose through the permute kernel
+    // work on the plain transpose A^T (n x m), made by the permute kernel
     TNB_TRY(ws_alloc(h, (size_t)m * n * sizeof(T), &At));
     if (lda != m) return set_err(h, TNB_ERR_UNSUPPORTED, "svd: lda != m with m < n");
     int64_t ext[2] = {m, n};
@@ -428,17 +455,17 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
   TNB_TRY(sort_desc(h, (const double*)nrm, jo.npad, (int*)perm, (double*)sorted, keys, pv, st));
   TNB_CUDA(h, cudaMemcpyAsync(S, sorted, ks * sizeof(double), cudaMemcpyDeviceToDevice, st));
   // left factor of the worked matrix = normalised G columns; right factor = V columns.
-  // A = Uw S Vw^H.  Not transposed: U = Uw, Vout = conj(Vw).  Transposed (worked on A^H = Uw S Vw^H
-  // => A = Vw S Uw^H): U = Vw, Vout = conj(Uw).
-  // With A = U S Vout^T we need Vout = conj(right singular vectors).
+  // Worked matrix = Uw S Vw^H with Uw = normalised G columns, Vw = accumulated rotations; the
+  // output convention is A = U S Vout^T.  Not transposed: U = Uw, Vout = conj(Vw).
   dim3 gU((unsigned)std::min<int64_t>((mm + 255) / 256, 64), (unsigned)kmax);
   dim3 gV((unsigned)std::min<int64_t>((nn + 255) / 256, 64), (unsigned)kmax);
   if (!transposed) {
     gather_cols_kernel<CPLX><<<gU, 256, 0, st>>>((T*)U, ldu, (const T*)jo.G, jo.ldg, mm, (const int*)perm, (const double*)nrm, 1, 0);
     gather_cols_kernel<CPLX><<<gV, 256, 0, st>>>((T*)V, ldv, (const T*)jo.V, jo.ldv, nn, (const int*)perm, nullptr, 0, 1);
   } else {
-    gather_cols_kernel<CPLX><<<gV, 256, 0, st>>>((T*)U, ldu, (const T*)jo.V, jo.ldv, nn, (const int*)perm, nullptr, 0, 0);
-    gather_cols_kernel<CPLX><<<gU, 256, 0, st>>>((T*)V, ldv, (const T*)jo.G, jo.ldg, mm, (const int*)perm, (const double*)nrm, 1, 1);
+    // worked on the plain transpose A^T = Uw S Vw^H  =>  A = conj(Vw) S Uw^T : U = conj(Vw), Vout = Uw
+    gather_cols_kernel<CPLX><<<gV, 256, 0, st>>>((T*)U, ldu, (const T*)jo.V, jo.ldv, nn, (const int*)perm, nullptr, 0, 1);
+    gather_cols_kernel<CPLX><<<gU, 256, 0, st>>>((T*)V, ldv, (const T*)jo.G, jo.ldg, mm, (const int*)perm, (const double*)nrm, 1, 0);
   }
   h->launches += 2;
   return check_cuda(h, cudaGetLastError(), "svd gather");

@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's ITensor-level interface for the hot path.
+
+Same names and argument meaning as the Julia API the reference plugs into (exports:
+``src/ITensorsGPU.jl:57-65``; overridden operations: ``src/ITensorsGPU.jl:32-43``), so the parity
+tests read like ``test/test_cuitensor.jl`` / ``test_cucontract.jl``.  Index bookkeeping (ids,
+tags, prime levels) stays on the host exactly as in the reference; every
+arithmetic operation is one call into libtnb200.so.  A CPU ITensor here is only a container for
+H2D/D2H (``cu`` / ``cpu``); there is no CPU arithmetic path.
+"""
+import itertools
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .ops import DTensor
+
+_ids = itertools.count(1)
+
+
+class Index:
+    """[EXT] ITensors ``Index``: (id, dim, tags, prime level)."""
+
+    __slots__ = ("id", "dim", "tags", "plev")
+
+    def __init__(self, dim, tags="", plev=0, id=None):
+        self.id = next(_ids) if id is None else id
+        self.dim = int(dim)
+        self.tags = tags
+        self.plev = int(plev)
+
+    def __eq__(self, o):
+        return isinstance(o, Index) and (self.id, self.plev) == (o.id, o.plev)
+
+    def __hash__(self):
+        return hash((self.id, self.plev))
+
+    def __repr__(self):
+        return "(dim=%d|id=%d|%s)%s" % (self.dim, self.id, self.tags, "'" * self.plev)
+
+    def prime(self, n=1):
+        return Index(self.dim, self.tags, self.plev + n, self.id)
+
+    def noprime(self):
+        return Index(self.dim, self.tags, 0, self.id)
+
+    def sim(self):
+        return Index(self.dim, self.tags, self.plev)
+
+
+def prime(x, *a, **k):
+    return x.prime(*a, **k)
+
+
+def dim(i):
+    return i.dim
+
+
+class Spectrum:
+    def __init__(self, eigs, truncerr):
+        self.eigs = eigs
+        self.truncerr = truncerr
+
+
+class ITensor:
+    """Dense ITensor.  ``store`` is a DTensor (GPU, ``CuDense``) or a NumPy array (CPU container)."""
+
+    def __init__(self, store, inds):
+        self.inds = tuple(inds)
+        dims = tuple(i.dim for i in self.inds)
+        if isinstance(store, DTensor):
+            if store.dims != dims:
+                store = DTensor(store.data, dims)
+        else:
+            store = np.asarray(store)
+            if store.shape != dims:
+                raise _lib.DimensionMismatch(2, "array of shape %s for indices of dims %s" % (store.shape, dims))
+        self.store = store
+
+    # ---- placement
+    @property
+    def on_gpu(self):
+        return isinstance(self.store, DTensor)
+
+    def _dev(self):
+        if not self.on_gpu:
+            raise _lib.TnbError(3, "arithmetic on a CPU ITensor: move it with cu(); there is no CPU path")
+        return self.store
+
+    def array(self):
+        """Logical ndarray on the host (``array(cpu(A))``)."""
+        return self.store.numpy() if self.on_gpu else np.array(self.store)
+
+    def scalar(self):
+        if len(self.inds) != 0:
+            raise _lib.DimensionMismatch(2, "scalar() of a rank-%d ITensor" % len(self.inds))
+        v = self.array().reshape(())
+        return complex(v) if np.iscomplexobj(v) else float(v)
+
+    # ---- index manipulation (host only)
+    def prime(self, n=1, which=None):
+        return ITensor(self.store, [i.prime(n) if (which is None or i == which) else i for i in self.inds])
+
+    def noprime(self):
+        return ITensor(self.store, [i.noprime() for i in self.inds])
+
+    def replaceinds(self, old, new):
+        m = dict(zip(old, new))
+        return ITensor(self.store, [m.get(i, i) for i in self.inds])
+
+    def dag(self):
+        s = self._dev()
+        if s.dtype == torch.complex128:
+            return ITensor(DTensor(torch.conj_physical(s.data), s.dims), self.inds)
+        return self
+
+    # ---- arithmetic: every op is one C-ABI call
+    def __mul__(self, o):
+        if isinstance(o, ITensor):
+            C, lc = ops.contract(self._dev(), self.inds, o._dev(), o.inds)        # contract!! (cudense.jl:83-110)
+            return ITensor(C, lc)
+        out = self._dev().clone()
+        if isinstance(o, complex) and out.dtype != torch.complex128:
+            out = out.astype(torch.complex128)
+        return ITensor(ops.scale(out, o), self.inds)                              # cudense.jl:22
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, x):
+        return self * (1.0 / x)                                                   # cudense.jl:502
+
+    def _addsub(self, o, sgn):
+        if set(self.inds) != set(o.inds) or len(self.inds) != len(o.inds):
+            raise _lib.DimensionMismatch(2, "cannot add ITensors with different index sets")
+        a, b = self._dev(), o._dev()
+        if a.dtype != b.dtype:
+            a, b = a.astype(torch.complex128), b.astype(torch.complex128)
+        out = a.clone()
+        ops.permute_axpby(b, o.inds, out, self.inds, alpha=sgn, beta=1.0)         # cudense.jl:333-445
+        return ITensor(out, self.inds)
+
+    def __add__(self, o):
+        return self._addsub(o, 1.0)
+
+    def __sub__(self, o):
+        return self._addsub(o, -1.0)
+
+    def __neg__(self):
+        return self * -1.0
+
+
+def norm(A):
+    return ops.norm(A._dev())                                                     # cudense.jl:27
+
+
+def dot(A, B):
+    """<A|B> = scalar(dag(A)*B)."""
+    if set(A.inds) != set(B.inds):
+        raise _lib.DimensionMismatch(2, "dot of ITensors with different index sets")
+    b = B if A.inds == B.inds else permute(B, A.inds)
+    a, bb = A._dev(), b._dev()
+    if a.dtype != bb.dtype:
+        a, bb = a.astype(torch.complex128), bb.astype(torch.complex128)
+    return ops.dot(a, bb)
+
+
+def permute(A, inds):
+    return ITensor(ops.permute(A._dev(), A.inds, tuple(inds)), inds)             # permute! (cudense.jl:447-478)
+
+
+def dag(A):
+    return A.dag()
+
+
+def noprime(A):
+    return A.noprime()
+
+
+def commonind(A, B):
+    c = [i for i in A.inds if i in B.inds]
+    return c[0] if c else None
+
+
+def delta(i, j, dtype=np.float64):
+    return cuITensor(np.eye(i.dim, j.dim, dtype=dtype), (i, j))
+
+
+# ---- constructors / transfer (src/cuitensor.jl)
+def cuITensor(x=None, inds=()):
+    """``cuITensor(inds...)`` zero-filled, ``cuITensor(x::Number, inds)`` constant, ``cuITensor(A::Array, inds)``
+    (``src/cuitensor.jl:1-26``)."""
+    inds = tuple(inds)
+    dims = tuple(i.dim for i in inds)
+    if x is None:
+        return ITensor(DTensor.zeros(dims), inds)
+    if np.isscalar(x):
+        return ITensor(DTensor.from_numpy(np.full(dims, x)), inds)
+    x = np.asarray(x)
+    if x.size != int(np.prod(dims, dtype=np.int64)):
+        raise _lib.DimensionMismatch(2, "array has %d elements, indices need %d" % (x.size, int(np.prod(dims))))
+    return ITensor(DTensor.from_numpy(x.reshape(dims, order="F") if x.shape != dims else x), inds)
+
+
+def randomCuITensor(*inds, dtype=np.float64, rng=None):
+    """``randomCuITensor`` (``src/cuitensor.jl:35-49``); values are drawn on the host and uploaded."""
+    rng = rng or np.random.default_rng()
+    dims = tuple(i.dim for i in inds)
+    a = rng.standard_normal(dims)
+    if np.issubdtype(dtype, np.complexfloating):
+        a = a + 1j * rng.standard_normal(dims)
+    return ITensor(DTensor.from_numpy(a), inds)
+
+
+def cu(x):
+    """``cu`` (``src/cuitensor.jl:28``, ``src/mps/cumps.jl:9``, ``src/mps/cumpo.jl:13``)."""
+    from . import mps as _mps
+    if isinstance(x, ITensor):
+        return x if x.on_gpu else ITensor(DTensor.from_numpy(x.store), x.inds)
+    if isinstance(x, (_mps.MPS, _mps.MPO)):
+        return x.cu()
+    raise TypeError("cu: unsupported %r" % type(x))
+
+
+def cpu(x):
+    """``cpu`` (``src/cuitensor.jl:30-33``, ``src/mps/cumpo.jl:25-31``)."""
+    from . import mps as _mps
+    if isinstance(x, ITensor):
+        return ITensor(x.array(), x.inds)
+    if isinstance(x, (_mps.MPS, _mps.MPO)):
+        return x.cpu()
+    raise TypeError("cpu: unsupported %r" % type(x))
+
+
+# ---- factorizations ([EXT] decomp.jl: combiner to rank 2, then the CuDense methods)
+def _matricize(A, Linds):
+    Linds = [i for i in Linds if i in A.inds]
+    Rinds = [i for i in A.inds if i not in Linds]
+    order = tuple(Linds) + tuple(Rinds)
+    T = A if A.inds == order else permute(A, order)          # the combiner's permute (K3)
+    m = int(np.prod([i.dim for i in Linds], dtype=np.int64))
+    n = int(np.prod([i.dim for i in Rinds], dtype=np.int64))
+    return DTensor(T._dev().data, (m, n)), tuple(Linds), tuple(Rinds)
+
+
+def svd(A, Linds, **kw):
+    """``U,S,V,spec = svd(A, Linds...; maxdim, mindim, cutoff)`` with ``A ~ U*S*V`` (CPU convention;
+    GPU body replaced: ``src/tensor/culinearalgebra.jl:33-72``).  S is a diagonal ITensor (dense here)."""
+    M, L, R = _matricize(A, Linds)
+    U, S, V, err = ops.svd(M, **kw)
+    k = U.dims[1]
+    u, v = Index(k, "Link,u"), Index(k, "Link,v")
+    Ut = ITensor(DTensor(U.data, tuple(i.dim for i in L) + (k,)), L + (u,))
+    Vt = ITensor(DTensor(V.data, tuple(i.dim for i in R) + (k,)), R + (v,))
+    St = ITensor(DTensor(torch.diag(S.to(A._dev().dtype)).reshape(-1).contiguous(), (k, k)), (u, v))
+    return Ut, St, Vt, Spectrum((S ** 2).cpu().numpy(), err)
+
+
+def eigen(A, Linds, Rinds, **kw):
+    """``D,U,spec = eigen(A, Linds, Rinds; ishermitian=true, ...)`` (``culinearalgebra.jl:74-108``)."""
+    kw.pop("ishermitian", None)
+    order = tuple(Linds) + tuple(Rinds)
+    T = A if A.inds == order else permute(A, order)
+    n = int(np.prod([i.dim for i in Linds], dtype=np.int64))
+    D, U, err = ops.eigh(DTensor(T._dev().data, (n, n)), **kw)
+    k = U.dims[1]
+    l, r = Index(k, "Link,eigen"), Index(k, "Link,eigen")
+    Ut = ITensor(DTensor(U.data, tuple(i.dim for i in Rinds) + (k,)), tuple(Rinds) + (r,))
+    Dt = ITensor(DTensor(torch.diag(D.to(A._dev().dtype)).reshape(-1).contiguous(), (k, k)), (l, r))
+    return Dt, Ut, Spectrum(D.cpu().numpy(), err)
+
+
+def qr(A, Linds):
+    """``Q,R = qr(A, Linds...)`` (``src/tensor/culinearalgebra.jl:110-121``)."""
+    M, L, R = _matricize(A, Linds)
+    Q, Rm = ops.qr(M)
+    k = Q.dims[1]
+    q = Index(k, "Link,qr")
+    return (ITensor(DTensor(Q.data, tuple(i.dim for i in L) + (k,)), L + (q,)),
+            ITensor(DTensor(Rm.data, (k,) + tuple(i.dim for i in R)), (q,) + R))
+
+
+def davidson(A, phi0, maxiter=2, miniter=1, errgoal=1e-14):
+    """[EXT] ITensors ``davidson(A, phi0; maxiter)`` on a callable ``A(v::ITensor)`` -- every vector
+    operation (``A(v)``, dot, axpy, norm) is a device call (``test/test_cuiterativesolvers.jl:13-28``)."""
+    phi = phi0 / norm(phi0)
+    V, AV = [phi], [A(phi)]
+    lam = dot(V[0], AV[0]).real if isinstance(dot(V[0], AV[0]), complex) else dot(V[0], AV[0])
+    q = AV[0] - V[0] * lam
+    M = np.array([[lam]], dtype=complex)
+    last = lam
+    for ni in range(1, maxiter + 1):
+        if norm(q) < 1e-12 and ni > miniter:
+            break
+        for _ in range(2):
+            for u in V:
+                q = q - u * dot(u, q)
+        qn = norm(q)
+        if qn < 1e-10:
+            break
+        q = q / qn
+        V.append(q)
+        AV.append(A(q))
+        k = len(V)
+        Mn = np.zeros((k, k), dtype=complex)
+        Mn[: k - 1, : k - 1] = M
+        for i in range(k):
+            Mn[i, k - 1] = dot(V[i], AV[k - 1])
+            Mn[k - 1, i] = np.conj(Mn[i, k - 1])
+        M = Mn
+        ev, U = np.linalg.eigh(M)
+        lam = float(ev[0])
+        y = U[:, 0]
+        cplx = any(v._dev().dtype == torch.complex128 for v in V + AV)
+        if not cplx:
+            y = y.real
+        phi = V[0] * complex(y[0]) if cplx else V[0] * float(y[0])
+        Aphi = AV[0] * (complex(y[0]) if cplx else float(y[0]))
+        for i in range(1, k):
+            c = complex(y[i]) if cplx else float(y[i])
+            phi = phi + V[i] * c
+            Aphi = Aphi + AV[i] * c
+        q = Aphi - phi * lam
+        if abs(lam - last) < errgoal and ni >= miniter and norm(q) < np.sqrt(errgoal):
+            break
+        last = lam
+    return lam, phi / norm(phi)

@@ -1,0 +1,308 @@
+"""Host-side mirror of the MPS / MPO level of the hot path: ``cu(psi)``, ``dmrg``, ``apply``,
+``inner``, ``orthogonalize`` ([EXT] ITensors.jl 0.2 algorithms the reference reaches through its
+overrides -- call sites ``examples/dmrg.jl:25``, ``examples/gate_evolution.jl:46``,
+``test/dmrg.jl:27,75``, ``test/test_cumps.jl``, ``test/test_cumpo.jl``).
+
+Fixed layouts (column-major flat buffers): MPS site ``A[l,s,r]``, MPO site ``W[a,s,s',b]`` (s = ket),
+environments ``L[l,l',a]`` / ``R[r,r',c]``.  All arithmetic is libtnb200.so calls; the sweep loop is
+host control flow only (which bond, which environment), like the Julia ``dmrg`` driver.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .ops import DTensor
+
+
+def _to_dev(a):
+    return a if isinstance(a, DTensor) else DTensor.from_numpy(a)
+
+
+def _to_host(a):
+    return a.numpy() if isinstance(a, DTensor) else np.asarray(a)
+
+
+class _Chain:
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+
+    def __len__(self):
+        return len(self.tensors)
+
+    def __getitem__(self, j):
+        return self.tensors[j]
+
+    def __setitem__(self, j, v):
+        self.tensors[j] = v
+
+    @property
+    def on_gpu(self):
+        return all(isinstance(t, DTensor) for t in self.tensors)
+
+    def _moved(self, f):
+        out = type(self).__new__(type(self))
+        out.__dict__.update(self.__dict__)
+        out.tensors = [f(t) for t in self.tensors]
+        return out
+
+    def cu(self):
+        """site-wise H2D (``cuMPS``/``cuMPO``: ``src/mps/cumps.jl:1-7``, ``src/mps/cumpo.jl:1-7``)."""
+        return self._moved(_to_dev)
+
+    def cpu(self):
+        """site-wise D2H (``cpu(::MPS/MPO)``: ``src/mps/cumpo.jl:25-31``)."""
+        return self._moved(_to_host)
+
+    def dims(self, j):
+        t = self.tensors[j]
+        return t.dims if isinstance(t, DTensor) else t.shape
+
+
+class MPS(_Chain):
+    """``llim``/``rlim`` as in ITensors: sites <= llim are left-orthogonal, sites >= rlim right-orthogonal."""
+
+    def __init__(self, tensors, llim=-1, rlim=None):
+        super().__init__(tensors)
+        self.llim = llim
+        self.rlim = len(self.tensors) if rlim is None else rlim
+
+    def maxlinkdim(self):
+        return max(self.dims(j)[2] for j in range(len(self) - 1)) if len(self) > 1 else 1
+
+    @property
+    def center(self):
+        return self.llim + 1 if self.rlim == self.llim + 2 else None
+
+
+class MPO(_Chain):
+    pass
+
+
+# ---- constructors (src/mps/cumps.jl, src/mps/cumpo.jl); values are made on the host and uploaded
+def cuMPS(psi):
+    return psi.cu()
+
+
+def cuMPO(H):
+    return H.cu()
+
+
+def productCuMPS(d, states):
+    """``productCuMPS(sites, states)`` (``src/mps/cumps.jl:58-134``): bond dimension 1 product state."""
+    ts = []
+    for s in states:
+        A = np.zeros((1, d, 1))
+        A[0, int(s), 0] = 1.0
+        ts.append(A)
+    return MPS(ts, llim=-1, rlim=1).cu()
+
+
+def randomCuMPS(N, d, chi=1, seed=None, dtype=np.float64):
+    """``randomCuMPS(sites)`` (``src/mps/cumps.jl:44-56``: bond dimension 1; ``chi`` generalises it).
+    Site tensors are random isometries, orthogonality centre at site 0."""
+    rng = np.random.default_rng(seed)
+    D = [int(min(chi, d ** min(k, N - k, 40))) for k in range(N + 1)]
+    ts = []
+    for j in range(N):
+        l, r = D[j], D[j + 1]
+        G = rng.standard_normal((d * r, l))
+        if np.issubdtype(dtype, np.complexfloating):
+            G = (G + 1j * rng.standard_normal((d * r, l))) / np.sqrt(2)
+        Q, _ = np.linalg.qr(G)
+        ts.append(np.ascontiguousarray(Q.T.reshape(l, d, r, order="F").astype(dtype)))
+    ts[0] = ts[0] / np.linalg.norm(ts[0])
+    return MPS(ts, llim=-1, rlim=1).cu()
+
+
+def randomCuMPO(N, d, seed=None):
+    """``randomCuMPO(sites)`` (``src/mps/cumpo.jl:15-23``): link dimension 1 only, like the reference."""
+    rng = np.random.default_rng(seed)
+    return MPO([rng.standard_normal((1, d, d, 1)) for _ in range(N)]).cu()
+
+
+# ---- measurements
+def inner(phi, psi, H=None):
+    """<phi|psi> or <phi|H|psi> (``test/test_cumps.jl:71-101``, ``test/test_cumpo.jl:42-91``)."""
+    if len(phi) != len(psi) or (H is not None and len(H) != len(psi)):
+        raise _lib.DimensionMismatch(2, "inner: chains of different length")
+    cplx = any(t.dtype == torch.complex128 for t in list(phi.tensors) + list(psi.tensors))
+    dt = torch.complex128 if cplx else torch.float64
+    if H is None:
+        E = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1))
+        for A, B in zip(phi.tensors, psi.tensors):
+            if A.dims[1] != B.dims[1]:
+                raise _lib.DimensionMismatch(2, "inner: site dimensions differ")
+            T, _ = ops.contract(E, ("lp", "l"), B.astype(dt), ("l", "s", "r"))
+            E, _ = ops.contract(A.astype(dt), ("lp", "s", "rp"), T, ("lp", "s", "r"), conj_a=True)
+        v = E.numpy().reshape(())
+    else:
+        E = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1, 1))
+        for A, W, B in zip(phi.tensors, H.tensors, psi.tensors):
+            if A is B or (A.data.data_ptr() == B.data.data_ptr()):
+                E = ops.env_update_left(E, B.astype(dt), W.astype(dt))
+            else:
+                T, _ = ops.contract(E, ("l", "lp", "a"), B.astype(dt), ("l", "s", "r"))
+                T, _ = ops.contract(T, ("lp", "a", "s", "r"), W.astype(dt), ("a", "s", "sp", "b"))
+                E, _ = ops.contract(T, ("lp", "r", "sp", "b"), A.astype(dt), ("lp", "sp", "rp"), lc=("r", "rp", "b"),
+                                    conj_b=True)
+        v = E.numpy().reshape(())
+    return complex(v) if cplx else float(v)
+
+
+def orthogonalize(psi, j):
+    """``orthogonalize!(psi, j)`` -- QR sweeps towards site j (``test/test_cumps.jl:138-149,200-229``)."""
+    ts = list(psi.tensors)
+    N = len(ts)
+    lo = min(max(psi.llim + 1, 0), j)          # sites <= llim are already left-orthogonal
+    hi = max(min(psi.rlim - 1, N - 1), j)      # sites >= rlim are already right-orthogonal
+    for b in range(lo, j):
+        l, d, r = ts[b].dims
+        Q, R = ops.qr(DTensor(ts[b].data, (l * d, r)))
+        k = Q.dims[1]
+        ts[b] = DTensor(Q.data, (l, d, k))
+        nxt, _ = ops.contract(R, ("k", "r"), ts[b + 1], ("r", "s", "rr"))
+        ts[b + 1] = nxt
+    for b in range(hi, j, -1):
+        l, d, r = ts[b].dims
+        At = ops.permute(DTensor(ts[b].data, (l, d * r)), ("l", "x"), ("x", "l"))     # (d r) x l
+        Q, R = ops.qr(At)
+        k = Q.dims[1]
+        ts[b] = DTensor(ops.permute(Q, ("x", "k"), ("k", "x")).data, (k, d, r))
+        prv, _ = ops.contract(ts[b - 1], ("ll", "s", "l"), R, ("k", "l"))            # R[k,l]: A_prev * R^T
+        ts[b - 1] = prv
+    return MPS(ts, llim=j - 1, rlim=j + 1)
+
+
+class Sweeps:
+    """[EXT] ``Sweeps(n)`` + ``maxdim!/mindim!/cutoff!/noise!`` (``examples/dmrg.jl:20-24``)."""
+
+    def __init__(self, nsweep, maxdim=(1,), mindim=(1,), cutoff=(0.0,), noise=(0.0,)):
+        self.nsweep = int(nsweep)
+
+        def ext(v):
+            v = list(np.atleast_1d(v))
+            return [v[min(i, len(v) - 1)] for i in range(self.nsweep)]
+        self.maxdim = [int(x) for x in ext(maxdim)]
+        self.mindim = [int(x) for x in ext(mindim)]
+        self.cutoff = [float(x) for x in ext(cutoff)]
+        self.noise = [float(x) for x in ext(noise)]
+
+    def __len__(self):
+        return self.nsweep
+
+
+def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None):
+    """``energy, psi = dmrg(H, psi0, sweeps)`` ([EXT] ITensors 0.2 two-site DMRG; reference call sites
+    ``examples/dmrg.jl:25``, ``test/dmrg.jl:27,75``).  Per bond: ONE fused C call (phi = A1*A2, Lanczos with
+    krylovdim matvecs, optional noise term, truncated factorization) plus one environment update."""
+    if not (H.on_gpu and psi0.on_gpu):
+        raise _lib.TnbError(3, "dmrg: move H and psi0 to the GPU with cu(); there is no CPU path")
+    N = len(psi0)
+    if len(H) != N:
+        raise _lib.DimensionMismatch(2, "dmrg: MPO and MPS lengths differ")
+    psi = orthogonalize(psi0, 0) if psi0.center != 0 else MPS(list(psi0.tensors), -1, 1)
+    ts = list(psi.tensors)
+    Ws = H.tensors
+    dt = torch.complex128 if any(t.dtype == torch.complex128 for t in ts + list(Ws)) else torch.float64
+    ts = [t.astype(dt) for t in ts]
+    Ws = [w.astype(dt) for w in Ws]
+    one = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1, 1))
+    Rs = [None] * N
+    Rs[N - 1] = one
+    for j in range(N - 1, 1, -1):
+        Rs[j - 1] = ops.env_update_right(Rs[j], ts[j], Ws[j])
+    Ls = [None] * N
+    Ls[0] = one
+    energy = None
+    for sw in range(sweeps.nsweep):
+        kw = dict(maxdim=sweeps.maxdim[sw], mindim=sweeps.mindim[sw], cutoff=sweeps.cutoff[sw],
+                  noise=sweeps.noise[sw], krylovdim=krylovdim, maxiter=maxiter, which_decomp=which_decomp)
+        maxerr = 0.0
+        for b in range(0, N - 1):
+            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls[b], Ws[b], Ws[b + 1], Rs[b + 1], ts[b], ts[b + 1],
+                                                               "left", **kw)
+            Ls[b + 1] = ops.env_update_left(Ls[b], ts[b], Ws[b])
+            maxerr = max(maxerr, err)
+            if observer:
+                observer(sw, b, "left", energy, err)
+        for b in range(N - 2, -1, -1):
+            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls[b], Ws[b], Ws[b + 1], Rs[b + 1], ts[b], ts[b + 1],
+                                                               "right", **kw)
+            Rs[b] = ops.env_update_right(Rs[b + 1], ts[b + 1], Ws[b + 1])
+            maxerr = max(maxerr, err)
+            if observer:
+                observer(sw, b, "right", energy, err)
+        if outputlevel > 0:
+            print("After sweep %d energy=%.12f maxlinkdim=%d maxerr=%.2E" %
+                  (sw + 1, energy, max(t.dims[2] for t in ts[:-1]), maxerr))
+    return energy, MPS(ts, llim=-1, rlim=1)
+
+
+def apply(gates, psi, cutoff=None, maxdim=None):
+    """``apply(gates, psi; cutoff, maxdim)`` ([EXT] ``product``; ``examples/gate_evolution.jl:46``).
+    gates: list of (G, n): one-site ``G[s',s]`` at site n, or two-site ``G[s1',s2',s1,s2]`` on (n, n+1)."""
+    if not psi.on_gpu:
+        raise _lib.TnbError(3, "apply: move psi to the GPU with cu(); there is no CPU path")
+    cur = psi
+    for G, n in gates:
+        G = _to_dev(G)
+        c = cur.center
+        if c != n:
+            cur = orthogonalize(cur, n)
+        ts = list(cur.tensors)
+        if len(G.dims) == 2:
+            A, _ = ops.contract(ts[n], ("l", "s", "r"), G, ("sp", "s"), lc=("l", "sp", "r"))
+            ts[n] = A
+            cur = MPS(ts, llim=n - 1, rlim=n + 1)
+        elif len(G.dims) == 4:
+            if n + 1 >= len(ts):
+                raise _lib.TnbError(1, "apply: two-site gate at the last site")
+            A1, A2, _ = ops.tebd_apply_gate(G, ts[n], ts[n + 1], maxdim=maxdim, cutoff=cutoff or 0.0)
+            ts[n], ts[n + 1] = A1, A2
+            cur = MPS(ts, llim=n, rlim=n + 2)
+        else:
+            raise _lib.TnbError(3, "apply: only one- and two-site gates")
+    return cur
+
+
+# ---- host-side model builders (inputs are made on the host and uploaded, like MPO(ampo, sites) then cu())
+def spin_ops(S):
+    d = int(round(2 * S + 1))
+    m = S - np.arange(d)
+    Sz = np.diag(m)
+    Sp = np.zeros((d, d))
+    for i in range(1, d):
+        Sp[i - 1, i] = np.sqrt(S * (S + 1) - m[i] * (m[i] + 1))
+    return dict(Sz=Sz, Sp=Sp, Sm=Sp.T.copy(), Sx=0.5 * (Sp + Sp.T), Id=np.eye(d), d=d)
+
+
+def _finish(Wb, N):
+    out = []
+    for j in range(N):
+        W = Wb
+        if j == 0:
+            W = W[-1:, :, :, :]
+        if j == N - 1:
+            W = W[:, :, :, :1]
+        out.append(np.ascontiguousarray(W))
+    return MPO(out)
+
+
+def heisenberg_mpo(N, S=0.5):
+    """sum_j Sz Sz + 1/2 (S+ S- + S- S+) (``examples/dmrg.jl:9-15``), MPO bond 5, W[a,s,s',b] = <s'|O|s>."""
+    o = spin_ops(S)
+    d = o["d"]
+    W = np.zeros((5, d, d, 5))
+    for (a, b, O) in [(0, 0, o["Id"]), (1, 0, o["Sm"]), (2, 0, o["Sp"]), (3, 0, o["Sz"]), (4, 1, 0.5 * o["Sp"]),
+                      (4, 2, 0.5 * o["Sm"]), (4, 3, o["Sz"]), (4, 4, o["Id"])]:
+        W[a, :, :, b] += O.T
+    return _finish(W, N)
+
+
+def tfim_mpo(N, J=-1.0, h=-0.5):
+    """J sum Sz Sz + h sum Sx (``test/dmrg.jl:63-67``), MPO bond 3."""
+    o = spin_ops(0.5)
+    W = np.zeros((3, 2, 2, 3))
+    for (a, b, O) in [(0, 0, o["Id"]), (1, 0, o["Sz"]), (2, 0, h * o["Sx"]), (2, 1, J * o["Sz"]), (2, 2, o["Id"])]:
+        W[a, :, :, b] += O.T
+    return _finish(W, N)

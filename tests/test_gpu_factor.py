@@ -56,12 +56,12 @@ def test_svd_rank_deficient_and_graded():
     U, S, V, err = tn.ops.svd(dev(B), cutoff=1e-20)
     assert len(S) <= 24
     assert ot.rel_err(U.numpy() @ np.diag(S.cpu().numpy()) @ V.numpy().T, B) < 1e-12
-    # graded singular values: one-sided Jacobi keeps small ones to high relative accuracy
+    # graded spectrum over 16 decades: absolute accuracy eps*sigma_max (a dense product cannot hold more)
     Q1, _ = np.linalg.qr(rand(rng, (64, 64), False)); Q2, _ = np.linalg.qr(rand(rng, (64, 64), False))
     s = 10.0 ** (-np.arange(64) / 4.0)
     A = (Q1 * s) @ Q2.T
     _, S, _, _ = tn.ops.svd(dev(A))
-    assert np.max(np.abs(S.cpu().numpy() - s) / s) < 1e-6
+    assert np.max(np.abs(S.cpu().numpy() - np.linalg.svd(A, compute_uv=False))) < 1e-15
 
 
 @pytest.mark.parametrize("cplx", [False, True])
@@ -160,7 +160,8 @@ def test_dmrg_bond_step_matches_oracle(ortho, noise, cutoff):
     assert A.shape == Ar.shape and B.shape == Br.shape
     got = np.tensordot(A, B, axes=(2, 0))
     want = np.tensordot(Ar, Br, axes=(2, 0))
-    assert ot.rel_err(got, want) < 1e-8
+    ph = np.vdot(want.ravel(), got.ravel())          # the eigenvector's global sign is free
+    assert ot.rel_err(got, want * ph / abs(ph)) < 1e-8
     assert err == pytest.approx(spec.truncerr, rel=1e-6, abs=1e-15)
 
 
