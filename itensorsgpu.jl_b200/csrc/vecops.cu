@@ -16,7 +16,7 @@ namespace tnb {
 // ------------------------------------------------------------------------------------
 // permute + axpby
 // ------------------------------------------------------------------------------------
-constexpr int MAXP = 12;
+constexpr int MAXP = 24;
 struct PermParams {
   int n;                 // modes after merging, in B order (mode 0 has unit stride in B)
   int ext[MAXP];
