@@ -203,8 +203,7 @@ def run_gpu(args):
         step = lambda: tn.ops.heff_apply(L, W1, W2, R, phi, out=out)
     else:
         # slab L[:, l'_shard, :] of this rank, made contiguous once (environments never move)
-        Ls = Lfull.view(W, chi, chi)[:, rank * clp:(rank + 1) * clp, :].contiguous()
-        L = tn.DTensor(Ls.reshape(-1), (chi, clp, W))
+        L = tn.DTensor(tn.shard.left_env_slab(Lfull, chi, W, rank, world), (chi, clp, W))
         del Lfull
         slab = tn.DTensor.empty((clp, D, D, chi))
         gathered = torch.empty(world * clp * D * D * chi, device="cuda", dtype=torch.float64)

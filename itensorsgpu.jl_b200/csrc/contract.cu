@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
     for (int e = 0; e < 2; ++e) {
       const int n = n0 + wn0 + j * 8 + lc * 2 + e;
       if (n >= p.N) continue;
-      const long long offn = decode<true>(p.gn, n);
+      long long offn;
+      if (p.splitN && n >= p.splitN) offn = decode<true>(p.gn, n - p.splitN) + (p.boffC2[blockIdx.y] - p.boffC[blockIdx.y]);
+      else offn = decode<true>(p.gn, n);
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         if (!okm[i]) continue;
@@ -647,8 +649,9 @@ int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64
                       const void* alpha, const void* A, int64_t lda, const long long* offA, long long strideA,
                       const void* B, int64_t ldb, const long long* offB, long long strideB, const void* beta,
                       void* C, int64_t ldc, const long long* offC, long long strideC, int batch,
-                      cudaStream_t st) {
+                      cudaStream_t st, int splitN, const long long* offC2) {
   if (m == 0 || n == 0 || batch == 0) return TNB_OK;
+  if (splitN && (!offC || !offC2)) return set_err(h, TNB_ERR_BAD_ARG, "gemm_batched: split output needs both offset tables");
   if (k < 1) return set_err(h, TNB_ERR_BAD_ARG, "gemm_batched: k < 1");
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -664,6 +667,7 @@ int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64
   p.batch = batch;
   p.boffA = offA; p.boffB = offB; p.boffC = offC;
   p.bstrideA = strideA; p.bstrideB = strideB; p.bstrideC = strideC;
+  p.splitN = splitN; p.boffC2 = offC2;
   return launch_planned(h, dtype, p, st);
 }
 

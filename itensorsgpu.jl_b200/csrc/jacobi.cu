@@ -25,8 +25,9 @@ namespace tnb {
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-template <bool CPLX> struct JT { using T = double; static constexpr int NB2 = 112; };
-template <> struct JT<true> { using T = double2; static constexpr int NB2 = 80; };
+template <bool CPLX> struct JT { using T = double; static constexpr int NB2 = 64; };
+template <> struct JT<true> { using T = double2; static constexpr int NB2 = 64; };
+constexpr int EIG_THREADS = 512;
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { /* conj(a)*b */ return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
@@ -35,9 +36,10 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { /* conj(a)*b */
 // small Hermitian eigensolver: one CTA per matrix, S and W resident in shared memory
 // ------------------------------------------------------------------------------------
 template <bool CPLX, int N>
-__global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<CPLX>::T* __restrict__ Sg,
-                                                             typename JT<CPLX>::T* __restrict__ Wg,
-                                                             double* offmax, int max_sweeps) {
+__global__ void __launch_bounds__(EIG_THREADS, 2) small_eigh_kernel(const typename JT<CPLX>::T* __restrict__ Sg,
+                                                                    typename JT<CPLX>::T* __restrict__ Wg,
+                                                                    double* offmax, const double* __restrict__ anorm,
+                                                                    int max_sweeps) {
   using T = typename JT<CPLX>::T;
   constexpr int LD = N + 1;
   constexpr int H = N / 2;
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
   __shared__ double rot_c[H], rot_s[H];
   __shared__ double2 rot_ph[H];   // e^{-i theta}
   __shared__ int flag;
+  __shared__ double tol_s;
   const int tid = threadIdx.x, nt = blockDim.x;
   const T* Sin = Sg + (size_t)blockIdx.x * N * N;
   T* Wout = Wg + (size_t)blockIdx.x * N * N;
@@ -60,6 +63,11 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
   __syncthreads();
   auto re = [](T v) -> double { if constexpr (CPLX) return v.x; else return v; };
   auto abs2 = [](T v) -> double { if constexpr (CPLX) return v.x * v.x + v.y * v.y; else return v * v; };
+  // Columns whose squared norm is below delta2 = (8 eps ||A||_F)^2 are numerically null: their content is
+  // rounding noise re-injected every time they meet a large column, so they can never converge in the
+  // relative sense.  Pairs of two null columns are left alone; a null column against a large one is
+  // measured against delta (LAPACK-class absolute accuracy eps*||A|| for the tiny singular values).
+  const double delta2 = anorm ? 3.2e-30 * anorm[0] * anorm[0] : 0.0;
 
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     // normalised off-diagonal maximum
@@ -67,9 +75,12 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
     for (int e = tid; e < N * N; e += nt) {
       const int i = e % N, j = e / N;
       if (i < j) {
-        const double d = re(S[i * LD + i]) * re(S[j * LD + j]);
+        const double di = re(S[i * LD + i]), dj = re(S[j * LD + j]);
         const double a = abs2(S[j * LD + i]);
-        if (a > 0.0) mx = fmax(mx, d > 0.0 ? a / d : 1e300);
+        if (a > 0.0 && !(di < delta2 && dj < delta2)) {
+          const double d = fmax(di, delta2) * fmax(dj, delta2);
+          mx = fmax(mx, d > 0.0 ? a / d : 1e300);
+        }
       }
     }
 #pragma unroll
@@ -84,7 +95,8 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
         // atomic max on a non-negative double via its bit pattern
         atomicMax((unsigned long long*)offmax, (unsigned long long)__double_as_longlong(fmin(m2, 1e300)));
       }
-      flag = (m2 < 1e-15) ? 1 : 0;
+      if (sweep == 0) tol_s = fmax(1e-15, 1e-4 * m2);   // adaptive inner tolerance: the outer sweeps finish the job
+      flag = (m2 < (sweep == 0 ? 1e-15 : tol_s)) ? 1 : 0;
     }
     __syncthreads();
     if (flag) break;
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
         const double g2 = abs2(spq);
         double c = 1.0, s = 0.0;
         double2 ph = make_double2(1.0, 0.0);
-        if (g2 > 0.0 && g2 > 1e-34 * fabs(app * aqq)) {
+        if (g2 > 0.0 && !(app < delta2 && aqq < delta2) && g2 > 1e-34 * fmax(app, delta2) * fmax(aqq, delta2)) {
           const double g = sqrt(g2);
           const double tau = (aqq - app) / (2.0 * g);
           const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
@@ -198,11 +210,11 @@ __global__ void __launch_bounds__(1024, 1) small_eigh_kernel(const typename JT<C
 // helper kernels
 // ------------------------------------------------------------------------------------
 template <typename T>
-__global__ void set_identity_kernel(T* V, long long rows, long long cols) {
+__global__ void set_identity_kernel(T* V, long long ld, long long rows, long long cols) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (long long)gridDim.x * blockDim.x) {
     const long long i = e % rows, j = e / rows;
-    if constexpr (sizeof(T) == 16) V[e] = make_double2(i == j ? 1.0 : 0.0, 0.0);
-    else V[e] = (i == j) ? 1.0 : 0.0;
+    if constexpr (sizeof(T) == 16) V[i + j * ld] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    else V[i + j * ld] = (i == j) ? 1.0 : 0.0;
   }
 }
 
@@ -275,29 +287,36 @@ __global__ void symmetrize_upper_kernel(typename JT<CPLX>::T* A, long long n) {
 // driver
 // ------------------------------------------------------------------------------------
 struct JacobiOut {
-  void* G;        // m x npad, converged (orthogonal columns)
-  void* V;        // n x npad accumulated rotations (A V = G), or null
+  void* G;        // converged columns (orthogonal), m rows, leading dimension ldg
+  void* V;        // accumulated rotations (A V = G), n rows, leading dimension ldv
   long long ldg, ldv;
   int npad;
 };
 
-size_t jacobi_ws_bytes(int dtype, int64_t m, int64_t n, bool want_v) {
-  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
-  const int b = NB2 / 2;
-  int64_t nblk = (n + b - 1) / b;
-  if (nblk & 1) ++nblk;
-  if (nblk < 2) nblk = 2;
-  const int64_t npad = nblk * b;
-  const size_t es = elsize(dtype);
-  size_t tot = 2 * al256((size_t)m * npad * es);
-  if (want_v) tot += 2 * al256((size_t)n * npad * es);
-  tot += 2 * al256((size_t)(nblk / 2) * NB2 * NB2 * es);   // S and W batches
-  tot += 4 * al256((size_t)nblk * sizeof(long long));      // offset tables
-  tot += al256(64);
-  return tot + 4096;
+static void jacobi_geometry(int dtype, int64_t n, int64_t* nblk, int64_t* npad) {
+  const int b = (dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2) / 2;
+  int64_t nb = (n + b - 1) / b;
+  if (nb & 1) ++nb;
+  if (nb < 2) nb = 2;
+  *nblk = nb;
+  *npad = nb * b;
 }
 
-// Runs the sweeps.  A (m x n, column-major, lda) is copied in; result buffers live in the arena.
+size_t jacobi_ws_bytes(int dtype, int64_t m, int64_t n, bool want_v) {
+  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
+  int64_t nblk, npad;
+  jacobi_geometry(dtype, n, &nblk, &npad);
+  const size_t es = elsize(dtype);
+  const int64_t mz = m + (want_v ? n : 0);
+  size_t tot = 2 * al256((size_t)mz * npad * es);
+  tot += 2 * al256((size_t)(nblk / 2) * NB2 * NB2 * es);   // S and W batches
+  tot += 2 * al256((size_t)nblk * sizeof(long long));      // offset tables
+  tot += 2 * al256(64);
+  return tot + 8192;
+}
+
+// Runs the sweeps on Z = [G; V] stacked in one (m+n) x npad matrix, so one batched GEMM rotates both.
+// A (m x n, column-major, lda) is copied in; result buffers live in the arena.
 template <bool CPLX>
 static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda, bool want_v, JacobiOut* out,
                       int* sweeps_done, cudaStream_t st) {
@@ -305,59 +324,47 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   constexpr int NB2 = JT<CPLX>::NB2;
   constexpr int b = NB2 / 2;
   const int dtype = CPLX ? TNB_C128 : TNB_F64;
-  int64_t nblk = (n + b - 1) / b;
-  if (nblk & 1) ++nblk;
-  if (nblk < 2) nblk = 2;
-  const int64_t npad = nblk * b;
+  int64_t nblk, npad;
+  jacobi_geometry(dtype, n, &nblk, &npad);
   const int k = (int)(nblk / 2);
   const size_t es = sizeof(T);
-  void *G0, *G1, *V0 = nullptr, *V1 = nullptr, *Sb, *Wb, *tA, *tB, *tCg, *tCv, *dscal;
-  TNB_TRY(ws_alloc(h, (size_t)m * npad * es, &G0));
-  TNB_TRY(ws_alloc(h, (size_t)m * npad * es, &G1));
-  if (want_v) {
-    TNB_TRY(ws_alloc(h, (size_t)n * npad * es, &V0));
-    TNB_TRY(ws_alloc(h, (size_t)n * npad * es, &V1));
-  }
+  const int64_t mz = m + (want_v ? n : 0);
+  void *Z0, *Z1, *Sb, *Wb, *tC1, *tC2, *dscal, *danorm;
+  TNB_TRY(ws_alloc(h, (size_t)mz * npad * es, &Z0));
+  TNB_TRY(ws_alloc(h, (size_t)mz * npad * es, &Z1));
   TNB_TRY(ws_alloc(h, (size_t)k * NB2 * NB2 * es, &Sb));
   TNB_TRY(ws_alloc(h, (size_t)k * NB2 * NB2 * es, &Wb));
-  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tA));
-  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tB));
-  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tCg));
-  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tCv));
+  TNB_TRY(ws_alloc(h, (size_t)k * sizeof(long long), &tC1));
+  TNB_TRY(ws_alloc(h, (size_t)k * sizeof(long long), &tC2));
   TNB_TRY(ws_alloc(h, 64, &dscal));
-  // G0 = [A 0]
-  TNB_CUDA(h, cudaMemsetAsync(G0, 0, (size_t)m * npad * es, st));
-  TNB_CUDA(h, cudaMemcpy2DAsync(G0, (size_t)m * es, A, (size_t)lda * es, (size_t)m * es, (size_t)n, cudaMemcpyDeviceToDevice, st));
+  TNB_TRY(ws_alloc(h, 64, &danorm));
+  // Z0 = [A 0; I]
+  TNB_CUDA(h, cudaMemsetAsync(Z0, 0, (size_t)mz * npad * es, st));
+  TNB_CUDA(h, cudaMemcpy2DAsync(Z0, (size_t)mz * es, A, (size_t)lda * es, (size_t)m * es, (size_t)n, cudaMemcpyDeviceToDevice, st));
   if (want_v) {
-    set_identity_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)V0, n, npad);
+    set_identity_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)Z0 + m, mz, n, npad);
     h->launches++;
   }
-  // offset tables for the rotate GEMMs: batch q = (pair p, half hf).  Destination slot of each
-  // half follows the round-robin rotation with slot 0 fixed (top row T_i = slot 2i, bottom B_i = 2i+1):
-  //   T_0 -> T_0 ; B_0 -> T_1 ; T_i -> T_{i+1} (1<=i<=k-2) ; T_{k-1} -> B_{k-1} ; B_i -> B_{i-1} (i>=1)
-  std::vector<long long> oa(nblk), ob(nblk), ocg(nblk), ocv(nblk);
-  for (int p = 0; p < k; ++p)
-    for (int hf = 0; hf < 2; ++hf) {
-      const int q = 2 * p + hf;
-      int dst;
-      if (k == 1) dst = q;
-      else if (hf == 0) dst = (p == 0) ? 0 : (p == k - 1 ? 2 * (k - 1) + 1 : 2 * (p + 1));
-      else dst = (p == 0) ? 2 : 2 * (p - 1) + 1;
-      oa[q] = (long long)p * NB2;               // in columns; scaled by ld below
-      ob[q] = (long long)p * NB2 * NB2 + (long long)hf * b * NB2;
-      ocg[q] = (long long)dst * b * m;
-      ocv[q] = (long long)dst * b * n;
+  // ||A||_F for the null-column threshold (contiguous input only; otherwise norm of the padded copy's top rows
+  // is the same number, computed column-block-wise by nrm2 over Z0 would include the identity -> use A)
+  if (lda == m) TNB_TRY(nrm2_impl(h, dtype, m * n, A, (double*)danorm, st));
+  else TNB_CUDA(h, cudaMemsetAsync(danorm, 0, 8, st));
+  // Destination slot of each half-pair follows the round-robin rotation with slot 0 fixed
+  // (top row T_p = slot 2p, bottom B_p = slot 2p+1):
+  //   T_0 -> T_0 ; B_0 -> T_1 ; T_p -> T_{p+1} (1<=p<=k-2) ; T_{k-1} -> B_{k-1} ; B_p -> B_{p-1} (p>=1)
+  std::vector<long long> oc1(k), oc2(k);
+  for (int p = 0; p < k; ++p) {
+    int d0, d1;
+    if (k == 1) { d0 = 0; d1 = 1; }
+    else {
+      d0 = (p == 0) ? 0 : (p == k - 1 ? 2 * (k - 1) + 1 : 2 * (p + 1));
+      d1 = (p == 0) ? 2 : 2 * (p - 1) + 1;
     }
-  std::vector<long long> oag(nblk), oav(nblk);
-  for (int q = 0; q < (int)nblk; ++q) { oag[q] = oa[q] * m; oav[q] = oa[q] * n; }
-  // tA holds G-side A offsets; V-side A offsets reuse tCv's buffer layout? keep separate small uploads
-  void* tAv;
-  TNB_TRY(ws_alloc(h, (size_t)nblk * sizeof(long long), &tAv));
-  TNB_CUDA(h, cudaMemcpyAsync(tA, oag.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
-  TNB_CUDA(h, cudaMemcpyAsync(tAv, oav.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
-  TNB_CUDA(h, cudaMemcpyAsync(tB, ob.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
-  TNB_CUDA(h, cudaMemcpyAsync(tCg, ocg.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
-  TNB_CUDA(h, cudaMemcpyAsync(tCv, ocv.data(), nblk * sizeof(long long), cudaMemcpyHostToDevice, st));
+    oc1[p] = (long long)d0 * b * mz;
+    oc2[p] = (long long)d1 * b * mz;
+  }
+  TNB_CUDA(h, cudaMemcpyAsync(tC1, oc1.data(), k * sizeof(long long), cudaMemcpyHostToDevice, st));
+  TNB_CUDA(h, cudaMemcpyAsync(tC2, oc2.data(), k * sizeof(long long), cudaMemcpyHostToDevice, st));
   TNB_CUDA(h, cudaStreamSynchronize(st));   // host vectors go out of scope below
 
   auto eig = small_eigh_kernel<CPLX, NB2>;
@@ -368,26 +375,23 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   const double tol = std::max(1e-14, std::sqrt((double)m) * 2.3e-16);
   const int steps = (k == 1) ? 1 : (int)nblk - 1;
   int cur = 0;
-  void* Gs[2] = {G0, G1};
-  void* Vs[2] = {V0, V1};
+  void* Zs[2] = {Z0, Z1};
   int sweep = 0;
   const int max_sweeps = 40;
   for (; sweep < max_sweeps; ++sweep) {
     TNB_CUDA(h, cudaMemsetAsync(dscal, 0, 8, st));
     for (int s = 0; s < steps; ++s) {
-      // 1. Gram of every pair
-      TNB_TRY(gemm_batched_impl(h, dtype, 'C', 'N', NB2, NB2, m, nullptr, Gs[cur], m, nullptr, (long long)NB2 * m,
-                                Gs[cur], m, nullptr, (long long)NB2 * m, nullptr, Sb, NB2, nullptr,
+      // 1. Gram of every pair (top m rows of Z only)
+      TNB_TRY(gemm_batched_impl(h, dtype, 'C', 'N', NB2, NB2, m, nullptr, Zs[cur], mz, nullptr, (long long)NB2 * mz,
+                                Zs[cur], mz, nullptr, (long long)NB2 * mz, nullptr, Sb, NB2, nullptr,
                                 (long long)NB2 * NB2, k, st));
       // 2. diagonalise
-      eig<<<k, 1024, SMEM, st>>>((const T*)Sb, (T*)Wb, (double*)dscal, 30);
+      eig<<<k, EIG_THREADS, SMEM, st>>>((const T*)Sb, (T*)Wb, (double*)dscal, (const double*)danorm, 30);
       h->launches++;
-      // 3. rotate G and V into next-step slots
-      TNB_TRY(gemm_batched_impl(h, dtype, 'N', 'N', m, b, NB2, nullptr, Gs[cur], m, (const long long*)tA, 0, Wb, NB2,
-                                (const long long*)tB, 0, nullptr, Gs[cur ^ 1], m, (const long long*)tCg, 0, (int)nblk, st));
-      if (want_v)
-        TNB_TRY(gemm_batched_impl(h, dtype, 'N', 'N', n, b, NB2, nullptr, Vs[cur], n, (const long long*)tAv, 0, Wb, NB2,
-                                  (const long long*)tB, 0, nullptr, Vs[cur ^ 1], n, (const long long*)tCv, 0, (int)nblk, st));
+      // 3. rotate [G;V] of every pair; the two halves land in their next-step slots
+      TNB_TRY(gemm_batched_impl(h, dtype, 'N', 'N', mz, NB2, NB2, nullptr, Zs[cur], mz, nullptr, (long long)NB2 * mz, Wb,
+                                NB2, nullptr, (long long)NB2 * NB2, nullptr, Zs[cur ^ 1], mz, (const long long*)tC1, 0, k,
+                                st, b, (const long long*)tC2));
       cur ^= 1;
     }
     TNB_CUDA(h, cudaGetLastError());
@@ -398,7 +402,7 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   if (sweeps_done) *sweeps_done = sweep;
   if (sweep >= max_sweeps && !(h->scal_host[100] < tol * 100))
     return set_err(h, TNB_ERR_NO_CONVERGENCE, "jacobi: no convergence after %d sweeps (off = %.3e)", sweep, h->scal_host[100]);
-  out->G = Gs[cur]; out->V = want_v ? Vs[cur] : nullptr; out->ldg = m; out->ldv = n; out->npad = (int)npad;
+  out->G = Zs[cur]; out->V = want_v ? (void*)((T*)Zs[cur] + m) : nullptr; out->ldg = mz; out->ldv = mz; out->npad = (int)npad;
   return TNB_OK;
 }
 
@@ -473,8 +477,8 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
 
 size_t svd_ws_bytes(int dtype, int64_t m, int64_t n) {
   const int64_t mm = std::max(m, n), nn = std::min(m, n);
-  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
-  const int64_t npad = ((nn + NB2 / 2 - 1) / (NB2 / 2) + 2) * (NB2 / 2);
+  int64_t nblk, npad;
+  jacobi_geometry(dtype, nn, &nblk, &npad);
   return jacobi_ws_bytes(dtype, mm, nn, true) + al256((size_t)m * n * elsize(dtype)) + 3 * al256(npad * 8) + 4096;
 }
 
@@ -536,8 +540,8 @@ static int eigh_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks, do
 }
 
 size_t eigh_ws_bytes(int dtype, int64_t n) {
-  const int NB2 = dtype == TNB_C128 ? JT<true>::NB2 : JT<false>::NB2;
-  const int64_t npad = ((n + NB2 / 2 - 1) / (NB2 / 2) + 2) * (NB2 / 2);
+  int64_t nblk, npad;
+  jacobi_geometry(dtype, n, &nblk, &npad);
   return jacobi_ws_bytes(dtype, n, n, true) + 5 * al256(npad * 8) + 4096;
 }
 

@@ -37,6 +37,9 @@ struct GemmParams {
   const long long* boffB;
   const long long* boffC;
   long long bstrideA, bstrideB, bstrideC;   // used when the corresponding boff* is null
+  // split output: columns n >= splitN of batch b go to C + boffC2[b] (column index n - splitN)
+  int splitN;
+  const long long* boffC2;
 };
 
 struct Handle {
@@ -93,7 +96,7 @@ int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64
                       const void* alpha, const void* A, int64_t lda, const long long* offA, long long strideA,
                       const void* B, int64_t ldb, const long long* offB, long long strideB, const void* beta,
                       void* C, int64_t ldc, const long long* offC, long long strideC, int batch,
-                      cudaStream_t st);
+                      cudaStream_t st, int splitN = 0, const long long* offC2 = nullptr);
 
 // ---- vector ops (vecops.cu)
 int permute_axpby_impl(Handle* h, int dtype, int n, const int64_t* extA, const int32_t* modeA,

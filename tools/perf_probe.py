@@ -96,6 +96,47 @@ def main():
             out.append(dict(what="cublas_zgemm", m=m, n=n, k=k, tflops=8.0 * m * n * k / best * 1e-12))
             print(json.dumps(out[-1]), flush=True)
             del A, B, Cc
+    if "factor" in which:
+        sizes = [int(x) for x in (sys.argv[sys.argv.index("--sizes") + 1].split(",") if "--sizes" in sys.argv else ["1024", "2048", "4096"])]
+        for n in sizes:
+            A = rnd(n * n).view(n, n)
+            M = tn.DTensor(A.reshape(-1).clone(), (n, n))
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            U, S, V, err = tn.ops.svd(M, maxdim=n // 2)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            out.append(dict(what="tnb_svd_trunc(maxdim n/2)", n=n, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
+            t0 = time.perf_counter(); torch.linalg.svd(A, full_matrices=False); torch.cuda.synchronize(); t1 = time.perf_counter()
+            out.append(dict(what="cusolver_svd(torch.linalg.svd)", n=n, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
+            X = rnd(n * (n // 2)).view(n, n // 2)
+            rho = (X @ X.t()).contiguous()
+            Mr = tn.DTensor(rho.reshape(-1).clone(), (n, n))
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            D, Ue, err = tn.ops.eigh(Mr, maxdim=n // 2)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            out.append(dict(what="tnb_eigh_trunc(psd rank n/2, maxdim n/2)", n=n, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
+            t0 = time.perf_counter(); torch.linalg.eigh(rho); torch.cuda.synchronize(); t1 = time.perf_counter()
+            out.append(dict(what="cusolver_syevd(torch.linalg.eigh)", n=n, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
+            Mq = tn.DTensor(A.reshape(-1)[: n * (n // 2)].clone(), (n, n // 2))
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            tn.ops.qr(Mq)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            out.append(dict(what="tnb_qr(n x n/2)", n=n, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
+            del A, M, X, rho, Mr, Mq
+    if "bond" in which:
+        sizes = [int(x) for x in (sys.argv[sys.argv.index("--sizes") + 1].split(",") if "--sizes" in sys.argv else ["512", "1024"])]
+        for chi in sizes:
+            d, w = 2, 5
+            L = tn.DTensor(rnd(chi * chi * w), (chi, chi, w)); R = tn.DTensor(rnd(chi * chi * w), (chi, chi, w))
+            W1 = tn.DTensor(rnd(w * d * d * w), (w, d, d, w)); W2 = tn.DTensor(rnd(w * d * d * w), (w, d, d, w))
+            A1 = tn.DTensor(rnd(chi * d * chi) / chi, (chi, d, chi)); A2 = tn.DTensor(rnd(chi * d * chi) / chi, (chi, d, chi))
+            for noise, cutoff, name in ((0.0, 0.0, "svd"), (1e-10, 1e-11, "eigen+noise")):
+                tn.ops.dmrg_bond_step(L, W1, W2, R, A1, A2, "left", maxdim=chi, cutoff=cutoff, noise=noise)
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                tn.ops.dmrg_bond_step(L, W1, W2, R, A1, A2, "left", maxdim=chi, cutoff=cutoff, noise=noise)
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                out.append(dict(what="dmrg_bond_step", branch=name, chi=chi, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
+            t0 = time.perf_counter(); tn.ops.env_update_left(L, A1, W1); torch.cuda.synchronize(); t1 = time.perf_counter()
+            out.append(dict(what="env_update_left", chi=chi, s=t1 - t0)); print(json.dumps(out[-1]), flush=True)
     if "vec" in which:
         n = 1 << 26
         x = tn.DTensor(rnd(n), (n,))
