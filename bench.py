@@ -315,7 +315,7 @@ def run_gpu(args):
                        "l2": "operands 0.5-2.7 GB per contraction, far larger than the 126 MB L2 (no flush needed)",
                        "parallelism": "single GPU" if world == 1 else "output bond l' sharded x%d + NCCL all-gather" % world},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": traffic, "kernel": "contract_kernel<f64,K-major,K-major,16B,128x128x16> (H_eff steps 1,4)",
+                         "traffic": traffic, "kernel": "contract_kernel<f64, A K-major, B K-major, 16-byte copies, Cfg<64x128x16, warp 32x64, 3 stages, 2 CTA/SM>> (H_eff steps 1 and 4)",
                          "flop_per_launch": flops_per_launch, "ms_per_launch": kern_s * 1e3, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": F / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,

@@ -1,0 +1,144 @@
+# TNB200.jl -- Julia glue that re-points the ITensorsGPU.jl hot-path overrides at libtnb200.so.
+#
+# UNTESTED HERE: the build container has no Julia (see DESIGN.md).  Every method below replaces the
+# BODY of a method the reference defines on CuDense storage (file:line cited per method, relative to
+# the ITensorsGPU.jl tree); signatures and return values are the reference's, so ITensors.jl keeps
+# dispatching to them unchanged.  `include` this file after `using ITensorsGPU`.
+module TNB200
+
+using CUDA, ITensors, ITensors.NDTensors, LinearAlgebra
+import ITensorsGPU: CuDense, CuDenseTensor
+import ITensors.NDTensors: ContractionProperties, Spectrum, Dense, Diag, Tensor, inds, dims, store, data, ind
+
+const LIB = get(ENV, "TNB200_LIB", "libtnb200.so")
+const HANDLE = Ref{Ptr{Cvoid}}(C_NULL)
+
+struct BondDims
+  chiL::Int64; chiR::Int64; d1::Int32; d2::Int32; wL::Int32; wM::Int32; wR::Int32
+end
+
+function handle()
+  if HANDLE[] == C_NULL
+    rc = ccall((:tnb_create, LIB), Cint, (Ref{Ptr{Cvoid}},), HANDLE)
+    rc == 0 || error("tnb_create failed ($rc): a B200 (sm_100) device is required; there is no CPU fallback")
+  end
+  return HANDLE[]
+end
+
+function check(rc::Cint)
+  rc == 0 && return
+  msg = unsafe_string(ccall((:tnb_last_error, LIB), Cstring, (Ptr{Cvoid},), handle()))
+  rc == 2 && throw(DimensionMismatch(msg))      # src/cuitensor.jl:55,72,78
+  rc == 1 && throw(ArgumentError(msg))          # src/mps/cumpo.jl:21
+  error("libtnb200: $msg")                      # src/tensor/cudense.jl:165
+end
+
+dtype(::Type{Float64}) = Cint(0)
+dtype(::Type{ComplexF64}) = Cint(1)
+stream() = CUDA.stream().handle                  # task-local stream, as CUDA.jl library wrappers use
+ptr(x::CuArray) = reinterpret(Ptr{Cvoid}, pointer(x))
+
+# ---- _contract!  (src/tensor/cudense.jl:238-331): mode labels come straight from ContractionProperties
+function NDTensors._contract!(CT::CuDenseTensor{El,NC}, AT::CuDenseTensor{El,NA}, BT::CuDenseTensor{El,NB},
+                              props::ContractionProperties, α::Number=one(El), β::Number=zero(El)) where {El,NC,NA,NB}
+  ea, eb, ec = Int64[dims(inds(AT))...], Int64[dims(inds(BT))...], Int64[dims(inds(CT))...]
+  # NDTensors labels: negative = contracted, positive = free; shift to non-negative ints
+  off = 1 - min(minimum(props.ai; init=0), minimum(props.bi; init=0))
+  ma, mb, mc = Int32.(props.ai .+ off), Int32.(props.bi .+ off), Int32.(props.ci .+ off)
+  a, b = Ref(El(α)), Ref(El(β))
+  check(ccall((:tnb_contract, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid},
+               Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+              handle(), dtype(El), NA, ea, ma, ptr(data(store(AT))), NB, eb, mb, ptr(data(store(BT))),
+              NC, ec, mc, ptr(data(store(CT))), a, b, 0, stream()))
+  return data(store(CT))                          # the reference returns parent(Cdata): cudense.jl:330
+end
+
+# ---- permute!  (src/tensor/cudense.jl:447-478)  and  + / -  (src/tensor/cudense.jl:333-445)
+function permute_axpby!(B::CuDenseTensor{El}, A::CuDenseTensor{El}, α, β) where {El}
+  n = length(inds(A))
+  modeA = Int32.(1:n)
+  modeB = Int32[findfirst(==(i), inds(A)) for i in inds(B)]
+  a, b = Ref(El(α)), Ref(El(β))
+  check(ccall((:tnb_permute_axpby, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(El), n, Int64[dims(inds(A))...], modeA, ptr(data(store(A))), modeB, ptr(data(store(B))), a, b, stream()))
+  return B
+end
+Base.permute!(B::CuDenseTensor, A::CuDenseTensor) = vec(data(store(permute_axpby!(B, A, 1, 0))))
+Base.:+(B::CuDenseTensor, A::CuDenseTensor) = permute_axpby!(B, A, 1, 1)
+Base.:-(B::CuDenseTensor, A::CuDenseTensor) = permute_axpby!(B, A, -1, 1)
+
+# ---- norm  (src/tensor/cudense.jl:27)
+function LinearAlgebra.norm(T::CuDenseTensor{El}) where {El}
+  r = Ref{Float64}(0)
+  check(ccall((:tnb_nrm2, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(El), length(data(store(T))), ptr(data(store(T))), C_NULL, r, stream()))
+  return r[]
+end
+
+# ---- truncate!  (src/tensor/cutruncate.jl:1-93) -- CPU rule, one kernel + one 24-byte readback
+function NDTensors.truncate!(P::CuVector{Float64}; kwargs...)
+  maxdim = Int64(get(kwargs, :maxdim, length(P))); mindim = Int64(get(kwargs, :mindim, 1))
+  cutoff = Float64(get(kwargs, :cutoff, 0.0))
+  flags = Cint((get(kwargs, :absoluteCutoff, get(kwargs, :use_absolute_cutoff, false)) ? 1 : 0) |
+               (get(kwargs, :doRelCutoff, get(kwargs, :use_relative_cutoff, true)) ? 0 : 2))
+  n, err, docut = Ref{Int64}(0), Ref{Float64}(0), Ref{Float64}(0)
+  check(ccall((:tnb_truncate, LIB), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Float64, Cint, Ref{Int64}, Ref{Float64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), ptr(P), length(P), maxdim, mindim, cutoff, flags, n, err, docut, stream()))
+  return err[], docut[], P[1:n[]]
+end
+
+# ---- svd  (src/tensor/culinearalgebra.jl:33-72).  Follows the CPU convention: A = U*S*V with V already conjugated.
+function LinearAlgebra.svd(T::CuDenseTensor{ElT,2,IndsT}; kwargs...) where {ElT,IndsT}
+  m, n = dims(T)
+  dotrunc = haskey(kwargs, :maxdim) || haskey(kwargs, :cutoff)
+  maxdim = Int64(get(kwargs, :maxdim, min(m, n))); kmax = dotrunc ? min(m, n, maxdim) : min(m, n)
+  A = copy(data(store(T)))
+  U, S, V = CUDA.zeros(ElT, m * kmax), CUDA.zeros(Float64, kmax), CUDA.zeros(ElT, n * kmax)
+  nk, err = Ref{Int64}(0), Ref{Float64}(0)
+  check(ccall((:tnb_svd_trunc, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Int64, Float64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+               Ref{Int64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), m, n, ptr(A), maxdim, Int64(get(kwargs, :mindim, 1)), Float64(get(kwargs, :cutoff, 0.0)),
+              0, dotrunc ? 1 : 0, ptr(U), ptr(S), ptr(V), nk, err, stream()))
+  k = nk[]
+  u = eltype(IndsT)(k); v = eltype(IndsT)(k)
+  return Tensor(Dense(U[1:m*k]), IndsT((ind(T, 1), u))), Tensor(Diag(S[1:k]), IndsT((u, v))),
+         Tensor(Dense(V[1:n*k]), IndsT((ind(T, 2), v))), Spectrum(S[1:k] .^ 2, err[])
+end
+
+# ---- eigen  (src/tensor/culinearalgebra.jl:74-108)
+function LinearAlgebra.eigen(T::Hermitian{ElT,<:CuDenseTensor{ElT,2,IndsT}}; kwargs...) where {ElT,IndsT}
+  n = dims(parent(T))[1]
+  dotrunc = haskey(kwargs, :maxdim) || haskey(kwargs, :cutoff)
+  maxdim = Int64(get(kwargs, :maxdim, n)); kmax = dotrunc ? min(n, maxdim) : n
+  A = copy(data(store(parent(T))))
+  D, U = CUDA.zeros(Float64, kmax), CUDA.zeros(ElT, n * kmax)
+  nk, err = Ref{Int64}(0), Ref{Float64}(0)
+  check(ccall((:tnb_eigh_trunc, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Int64, Int64, Float64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), n, ptr(A), maxdim, Int64(get(kwargs, :mindim, 1)), Float64(get(kwargs, :cutoff, 0.0)),
+              0, dotrunc ? 1 : 0, ptr(D), ptr(U), nk, err, stream()))
+  k = nk[]
+  l = eltype(IndsT)(k); r = eltype(IndsT)(k)
+  return Tensor(Diag(D[1:k]), IndsT((l, dag(r)))), Tensor(Dense(U[1:n*k]), IndsT((dag(ind(parent(T), 2)), dag(r)))), Spectrum(D[1:k], err[])
+end
+
+# ---- qr  (src/tensor/culinearalgebra.jl:110-121)
+function LinearAlgebra.qr(T::CuDenseTensor{ElT,2,IndsT}; kwargs...) where {ElT,IndsT}
+  m, n = dims(T); k = min(m, n)
+  Q, R = CUDA.zeros(ElT, m * k), CUDA.zeros(ElT, k * n)
+  check(ccall((:tnb_qr, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), m, n, ptr(data(store(T))), ptr(Q), ptr(R), stream()))
+  q = eltype(IndsT)(k)
+  return Tensor(Dense(Q), IndsT((ind(T, 1), q))), Tensor(Dense(R), IndsT((q, ind(T, 2))))
+end
+
+# ---- fused tier: product(::ProjMPO, ::ITensor) for the two-site case ([EXT] ITensors src/mps/projmpo.jl)
+# The glue permutes L, R, W_b, W_{b+1} once per `position!` into the fixed layouts of include/tnb200.h and then
+# calls tnb_heff_apply; kept out of this file's executable part because ProjMPO internals differ between
+# ITensors 0.2.x patch releases -- see INTEGRATION.md for the call.
+
+end # module
