@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace tnb {
 
@@ -135,6 +136,19 @@ static int factorize_core(Handle* h, int dtype, int64_t m, int64_t n, void* M, i
   if (which == TNB_DECOMP_AUTO) {
     if (rho_pert) which = TNB_DECOMP_EIGEN;
     else which = (cutoff <= 1e-12) ? TNB_DECOMP_SVD : TNB_DECOMP_EIGEN;
+  }
+  // Large svd-branch bonds go through the Gram matrix of the side that must become the isometry
+  // (rho = M M^H for ortho left, M^H M for ortho right; only when that side is the smaller one, so rho has
+  // full rank and kmax is unchanged): U from the fast Hermitian eigensolver, the other factor by projection.
+  // This is exactly what [EXT] factorize's own eigen branch computes; singular values below sqrt(eps)*s_max
+  // are then resolved to absolute accuracy eps*|M|^2 only, i.e. weights that cannot move an energy at the
+  // 1e-10 bar (tests/test_gpu_dmrg.py runs the DMRG parity cases through this route as well).
+  // TNB_SVD_GRAM_MIN (default 1024) sets the size from which it applies; 0 disables it.
+  if (which == TNB_DECOMP_SVD && !rho_pert) {
+    const char* ev = getenv("TNB_SVD_GRAM_MIN");
+    const int64_t gmin = ev ? atoll(ev) : 1024;
+    const bool side_ok = (ortho == TNB_ORTHO_LEFT) ? (m <= n) : (n <= m);
+    if (gmin > 0 && kfull >= gmin && side_ok) which = TNB_DECOMP_EIGEN;
   }
   int64_t nk = kfull;
   double err = 0.0;

@@ -18,6 +18,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <numeric>
 #include <vector>
 
@@ -539,13 +541,29 @@ static int eigh_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks, do
   return check_cuda(h, cudaGetLastError(), "eigh gather");
 }
 
+// n >= EIGH_DC_MIN: tridiagonalisation + divide & conquer (eigh_dc.cu); below: Jacobi (high relative accuracy,
+// launch-latency bound anyway).  TNB_EIGH=jacobi|dc overrides (A/B measurements).
+constexpr int64_t EIGH_DC_MIN = 128;
+size_t eigh_dc_ws_bytes(int dtype, int64_t n, int64_t kmax);
+int eigh_dc_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu,
+                 cudaStream_t st);
+static bool eigh_use_dc(int64_t n) {
+  const char* e = getenv("TNB_EIGH");     // read per call: tests flip it inside one process
+  const int mode = (e && !strcmp(e, "jacobi")) ? 1 : (e && !strcmp(e, "dc")) ? 2 : 0;
+  if (mode == 1) return false;
+  if (mode == 2) return n >= 2;
+  return n >= EIGH_DC_MIN;
+}
+
 size_t eigh_ws_bytes(int dtype, int64_t n) {
   int64_t nblk, npad;
   jacobi_geometry(dtype, n, &nblk, &npad);
-  return jacobi_ws_bytes(dtype, n, n, true) + 5 * al256(npad * 8) + 4096;
+  const size_t jac = jacobi_ws_bytes(dtype, n, n, true) + 5 * al256(npad * 8) + 4096;
+  return eigh_use_dc(n) ? eigh_dc_ws_bytes(dtype, n, n) : jac;
 }
 
 int eigh_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu, cudaStream_t st) {
+  if (eigh_use_dc(n)) return eigh_dc_impl(h, dtype, n, A, kmax, ks, D, U, ldu, st);
   if (dtype == TNB_F64) return eigh_core<false>(h, n, A, kmax, ks, D, U, ldu, st);
   if (dtype == TNB_C128) return eigh_core<true>(h, n, A, kmax, ks, D, U, ldu, st);
   return set_err(h, TNB_ERR_UNSUPPORTED, "eigh: dtype %d", dtype);

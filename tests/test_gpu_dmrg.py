@@ -207,3 +207,44 @@ def test_davidson_itensor_map(cplx_start):
     lam, v = tn.davidson(M, v0, maxiter=10)
     r = M(v) - v * complex(lam)
     assert tn.norm(r) < 1e-6 * abs(lam)
+
+
+def _generic_heisenberg(N, seed=3):
+    Ws = models.heisenberg_mpo(N, 0.5)
+    rng = np.random.default_rng(seed)
+    Sz = np.diag([0.5, -0.5])
+    for j in range(N):
+        Wj = Ws[j].copy()
+        Wj[Wj.shape[0] - 1, :, :, 0] += 0.3 * rng.standard_normal() * Sz.T
+        Ws[j] = Wj
+    return Ws
+
+
+@pytest.mark.parametrize("route", ["eigen_dc", "svd_gram", "small_forced"])
+def test_dmrg_strict_parity_fast_eigensolver(route, monkeypatch):
+    """Same 1e-10 bar with the factorization going through the tridiagonalisation + divide & conquer
+    eigensolver (csrc/tridiag.cu, stedc.cu): (i) eigen branch at chi = 64 (rho is 128 x 128, the default
+    switch-over size), (ii) svd branch routed through the Gram matrix (what chi = 4096 bonds use),
+    (iii) both forced on at tiny sizes so that every bond of the sweep, edges included, takes them."""
+    from itensorsgpu_b200 import tn
+    if route == "small_forced":
+        monkeypatch.setenv("TNB_EIGH", "dc")
+        monkeypatch.setenv("TNB_SVD_GRAM_MIN", "2")
+        N, kw, which = 12, dict(maxdim=[8, 12, 16], cutoff=0.0), None
+    elif route == "svd_gram":
+        monkeypatch.setenv("TNB_SVD_GRAM_MIN", "64")
+        N, kw, which = 16, dict(maxdim=[16, 32, 64], cutoff=0.0), None
+    else:
+        # eigen branch: a relative cutoff of 1e-13 drops the numerically-null eigenvectors of rank-deficient
+        # rho (edge bonds), whose choice is implementation-defined; the kept weight then agrees to ~1e-13
+        N, kw, which = 16, dict(maxdim=[16, 32, 64], cutoff=1e-13), "eigen"
+    Ws = _generic_heisenberg(N)
+    psi0 = omps.random_mps(N, 2, 4, np.random.default_rng(5))
+    e_ref, _, hist_ref = od.dmrg(Ws, psi0, od.Sweeps(3, **kw), which_decomp=which)
+    hist = []
+    e, psi = tn.dmrg(tn.cu(_host_mpo(tn, Ws)), tn.cu(_host_mps(tn, psi0)), tn.Sweeps(3, **kw), which_decomp=which,
+                     observer=lambda sw, b, o, en, err: hist.append(en) if (o == "right" and b == 0) else None)
+    assert np.max(np.abs(np.array(hist) - np.array(hist_ref))) < 1e-10
+    assert abs(e - e_ref) < 1e-10
+    for t in psi.cpu().tensors[1:]:
+        assert omps.right_orthogonality_error(t) < 1e-11
