@@ -168,6 +168,58 @@ def measure_fp64_peak():
     return 37.2, "fallback: 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (microbenchmark unavailable)"
 
 
+def sweep_sample(tn, chi, branch):
+    """Bounded sample of metric M1 (sweep seconds): one real two-site DMRG sweep through the public dmrg() on a
+    SHORT S=1/2 Heisenberg chain whose bonds take every (chiL, chiR) shape of the N=100 chain (bond dims
+    min(2^k, 2^(N-k), chi)); the N=100 sweep time is then re-assembled bond by bond from the measured
+    per-shape times (198 bond steps).  tools/sweep_c3.py measures the full N=100 sweep directly
+    (profiles/*_sweep_c3_*.json)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from sweep_c3 import random_iso_mps
+    lg = max(1, (chi - 1).bit_length())
+    Ns = 2 * lg + 4                      # three full-size bonds per half sweep
+    psi, Dm = random_iso_mps(Ns, 2, chi)
+    H = tn.cu(tn.heisenberg_mpo(Ns, 0.5))
+    kw = dict(maxdim=chi, cutoff=0.0, noise=0.0) if branch == "svd" else dict(maxdim=chi, cutoff=1e-11, noise=1e-10)
+    marks = []
+    h = tn.handle()
+    l0 = h.launches
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e, _ = tn.dmrg(H, psi, tn.Sweeps(1, **kw), observer=lambda sw, b, o, en, err: marks.append((b, o, time.perf_counter())))
+    torch.cuda.synchronize()
+    total = time.perf_counter() - t0
+    per = {}
+    prev = t0
+    first = True
+    for (b, o, now) in marks:
+        if not first:                    # the first callback also contains the right-environment build
+            per.setdefault((o, Dm[b], Dm[b + 2]), []).append(now - prev)
+        first = False
+        prev = now
+    tshape = {k: min(v) for k, v in per.items()}
+    # re-assemble the N=100 chain
+    N = 100
+    D100 = [int(min(chi, 2 ** min(k, N - k, 40))) for k in range(N + 1)]
+    est, missing = 0.0, 0
+    for o in ("left", "right"):
+        for b in range(N - 1):
+            key = (o, D100[b], D100[b + 2])
+            if key in tshape:
+                est += tshape[key]
+            else:
+                missing += 1
+    full = [tshape.get((o, chi, chi)) for o in ("left", "right")]
+    return {"seconds_N100_reassembled": est, "bond_steps": 2 * (N - 1), "shapes_missing": missing,
+            "central_bond_step_ms": [None if x is None else x * 1e3 for x in full],
+            "branch": branch, "params": kw, "energy_after_sample_sweep": e,
+            "sample": "one full DMRG sweep on a %d-site chain (all (chiL,chiR) shapes of the N=100 chain at maxdim %d), "
+                      "%.1f s incl. environment build; per-shape bond-step times (bond step + environment update, "
+                      "host clock around synchronous C calls) summed over the 198 bonds of N=100" % (Ns, chi, total),
+            "gpu_launches": h.launches - l0}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -299,6 +351,11 @@ def run_gpu(args):
             ctf, ctot = cpu_heff_tflops(cchi, 2, warm=0)
             cpu = {"value": ctf, "unit": UNIT, "cores": host_threads(), "kind": "port",
                    "sample": "oracle (NumPy/OpenBLAS dgemm) H_eff*phi at chi=%d, 2 applies, %.1f s" % (cchi, ctot)}
+        sweep = None
+        if world == 1 and not args.no_sweep:
+            del L, R, phi, out
+            torch.cuda.empty_cache()
+            sweep = sweep_sample(tn, chi, args.sweep_branch)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -321,6 +378,7 @@ def run_gpu(args):
             "e2e": {"value": F / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "ms_per_step": e2e_s * 1e3},
             "gpu_launches": launches,
+            "sweep": sweep,
             "clocks": clocks,
             "heff_frac_of_fp64_peak": value / (peak * world),
         }
@@ -337,6 +395,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chi", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the DMRG sweep-seconds sample (metric M1)")
+    ap.add_argument("--sweep-branch", default="svd", choices=["svd", "eigen"],
+                    help="factorize rule of the sweep sample: svd = cutoff 0 / noise 0 (C3), eigen = cutoff 1e-11 / noise 1e-10")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -222,6 +222,8 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
             energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls[b], Ws[b], Ws[b + 1], Rs[b + 1], ts[b], ts[b + 1],
                                                                "left", **kw)
             Ls[b + 1] = ops.env_update_left(Ls[b], ts[b], Ws[b])
+            if b + 1 < N - 1:
+                Rs[b + 1] = None      # stale now (site b+1 changed); freeing it keeps one environment per bond resident
             maxerr = max(maxerr, err)
             if observer:
                 observer(sw, b, "left", energy, err)
@@ -229,6 +231,8 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
             energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls[b], Ws[b], Ws[b + 1], Rs[b + 1], ts[b], ts[b + 1],
                                                                "right", **kw)
             Rs[b] = ops.env_update_right(Rs[b + 1], ts[b + 1], Ws[b + 1])
+            if b > 0:
+                Ls[b] = None
             maxerr = max(maxerr, err)
             if observer:
                 observer(sw, b, "right", energy, err)
