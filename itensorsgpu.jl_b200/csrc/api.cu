@@ -87,6 +87,7 @@ int tnb_create(tnb_handle_t* out) {
       cudaMallocHost((void**)&hd->scal_host, 256 * sizeof(double)) != cudaSuccess ||
       cudaMalloc((void**)&hd->partials, 8 * RED_MAX_BLOCKS * sizeof(double)) != cudaSuccess ||
       cudaMalloc((void**)&hd->counter, 64) != cudaSuccess ||
+      cudaMalloc(&hd->what, 64 * 1024) != cudaSuccess ||
       cudaStreamCreateWithFlags(&hd->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete hd;
     return TNB_ERR_ALLOC;
@@ -104,6 +105,7 @@ int tnb_destroy(tnb_handle_t h) {
   if (H->scal) cudaFree(H->scal);
   if (H->partials) cudaFree(H->partials);
   if (H->counter) cudaFree(H->counter);
+  if (H->what) cudaFree(H->what);
   if (H->scal_host) cudaFreeHost(H->scal_host);
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
   delete H;

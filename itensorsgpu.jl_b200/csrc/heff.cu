@@ -9,12 +9,101 @@
 // (src/tensor/cudense.jl:62-72), no descriptor/plan rebuild per call (cudense.jl:255-294)
 // and no blocking D2H per dot/norm (cudense.jl:25-27): temporaries live in the handle's
 // arena and every Lanczos scalar stays on the device until one final readback.
+#include "tnb_arith.cuh"
 #include "tnb_internal.h"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 namespace tnb {
+
+// ------------------------------------------------------------------------------------
+// H_eff steps 2+3 fused: T3[r,l',s1',s2',c] = sum_{a,s1,s2} T1[s1,s2,r,l',a] * What[(s1,s2,a),(s1',s2',c)],
+// What = sum_b W1[a,s1,s1',b] W2[b,s2,s2',c].  K = w d^2 = 20: pure HBM streaming (read T1 once, write T3 once,
+// 2 * 8 * d^2 w chi^2 bytes), one "pixel" (r,l') per thread, What broadcast from shared memory.
+// The reference issues these as two cuTENSOR contractions with a full-size intermediate
+// (src/tensor/cudense.jl:238-331 twice + the allocation/zero-fill at :62-72).
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void what_kernel(const T* __restrict__ W1, const T* __restrict__ W2, T* What, int wl, int wm, int wr, int d1, int d2) {
+  const int NI = wl * d1 * d2, NO = d1 * d2 * wr;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NI * NO; e += gridDim.x * blockDim.x) {
+    const int i = e / NO, o = e % NO;
+    const int s1 = i % d1, s2 = (i / d1) % d2, a = i / (d1 * d2);
+    const int s1p = o % d1, s2p = (o / d1) % d2, c = o / (d1 * d2);
+    T acc = a_zero<T>();
+    for (int b = 0; b < wm; ++b)
+      acc = a_add(acc, a_mul(W1[a + wl * (s1 + d1 * (s1p + d1 * b))], W2[b + wm * (s2 + d2 * (s2p + d2 * c))]));
+    What[e] = acc;
+  }
+}
+
+template <bool CPLX, int D, int W>
+__global__ void __launch_bounds__(256) heff23_kernel(const typename ElemT<CPLX>::T* __restrict__ T1,
+                                                      const typename ElemT<CPLX>::T* __restrict__ What,
+                                                      typename ElemT<CPLX>::T* __restrict__ T3, long long npix) {
+  using T = typename ElemT<CPLX>::T;
+  constexpr int Q = D * D, NI = W * Q, NO = Q * W;
+  __shared__ __align__(16) T Ws[NI * NO];
+  for (int e = threadIdx.x; e < NI * NO; e += 256) Ws[e] = What[e];
+  __syncthreads();
+  // exactly one pixel per thread: with a pixel loop the compiler hoists all NI*NO What loads out of it and spills
+  const long long x = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (x < npix) {
+    T in[NI];
+#pragma unroll
+    for (int a = 0; a < W; ++a) {
+      const T* src = T1 + (size_t)Q * (x + npix * a);
+      if constexpr (!CPLX && (Q % 2 == 0)) {
+#pragma unroll
+        for (int q = 0; q < Q; q += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(src + q);
+          in[a * Q + q] = v.x; in[a * Q + q + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) in[a * Q + q] = src[q];
+      }
+    }
+    T acc[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[o] = a_zero<T>();
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        if constexpr (CPLX) acc[o] = a_add(acc[o], a_mul(in[i], Ws[i * NO + o]));
+        else acc[o] = fma(in[i], Ws[i * NO + o], acc[o]);
+      }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) T3[x + npix * o] = acc[o];
+  }
+}
+
+// returns 1 if the fused kernel handled steps 2+3 (t_in -> t_out), 0 if the shape has no instantiation
+static int heff23_fused(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* W1, const void* W2,
+                        const void* t_in, void* t_out, void* what, cudaStream_t st) {
+  static const bool off = getenv("TNB_HEFF23") && !strcmp(getenv("TNB_HEFF23"), "off");
+  if (off || d->d1 != d->d2 || d->wL != d->wR) return 0;
+  const long long npix = (long long)d->chiR * clp;
+  if ((npix + 255) / 256 > 2147483647LL) return 0;
+  const int grid = (int)((npix + 255) / 256);
+  const bool c = dtype == TNB_C128;
+  const int D = d->d1, W = d->wL;
+  if (!((D == 2 && (W == 5 || W == 3)) || (D == 3 && W == 5 && !c))) return 0;
+  const int ne = (W * D * D) * (D * D * W);
+  if (c) what_kernel<double2><<<(ne + 255) / 256, 256, 0, st>>>((const double2*)W1, (const double2*)W2, (double2*)what, d->wL, d->wM, d->wR, D, D);
+  else what_kernel<double><<<(ne + 255) / 256, 256, 0, st>>>((const double*)W1, (const double*)W2, (double*)what, d->wL, d->wM, d->wR, D, D);
+#define TNB_H23(C, DD, WW) heff23_kernel<C, DD, WW><<<grid, 256, 0, st>>>((const typename ElemT<C>::T*)t_in, (const typename ElemT<C>::T*)what, (typename ElemT<C>::T*)t_out, npix)
+  if (D == 2 && W == 5) { if (c) TNB_H23(true, 2, 5); else TNB_H23(false, 2, 5); }
+  else if (D == 2 && W == 3) { if (c) TNB_H23(true, 2, 3); else TNB_H23(false, 2, 3); }
+  else TNB_H23(false, 3, 5);
+#undef TNB_H23
+  h->launches += 2;
+  return 1;
+}
 
 enum { mL = 0, mS1, mS2, mR, mLp, mA, mS1p, mB, mS2p, mC, mRp, mLpp, mS1pp, mS2pp, mRpp };
 
@@ -38,6 +127,14 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
     int64_t eb[] = {cl, clp, wl};    int32_t mb[] = {mL, mLp, mA};
     int64_t ec[] = {d1, d2, cr, clp, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
     TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+  }
+  // 2+3 fused (one streaming pass) when the shape has an instantiation
+  if (heff23_fused(h, dtype, d, clp, W1, W2, t0, t1, h->what, st)) {
+    int64_t ea[] = {cr, clp, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t eb[] = {cr, cr, wr};          int32_t mb[] = {mR, mRp, mC};
+    int64_t ec[] = {clp, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
+    TNB_TRY(check_cuda(h, cudaGetLastError(), "heff23"));
+    return contract_impl(h, dtype, 5, ea, ma, t1, 3, eb, mb, R, 4, ec, mc, out, nullptr, nullptr, 0, st);
   }
   {  // 2. T2[s2,r,l',s1',b] = T1 W1[a,s1,s1',b]
     int64_t ea[] = {d1, d2, cr, clp, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};

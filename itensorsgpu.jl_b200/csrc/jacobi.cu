@@ -541,9 +541,11 @@ static int eigh_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks, do
   return check_cuda(h, cudaGetLastError(), "eigh gather");
 }
 
-// n >= EIGH_DC_MIN: tridiagonalisation + divide & conquer (eigh_dc.cu); below: Jacobi (high relative accuracy,
-// launch-latency bound anyway).  TNB_EIGH=jacobi|dc overrides (A/B measurements).
-constexpr int64_t EIGH_DC_MIN = 128;
+// n >= EIGH_DC_MIN: tridiagonalisation + divide & conquer (eigh_dc.cu): LAPACK-class absolute accuracy and no
+// convergence hazard.  (One-sided Jacobi ON rho squares the conditioning: columns lambda_j v_j of a noisy
+// rank-deficient density matrix stall at relative off-diagonals ~eps*lambda_max/lambda_j.)  Jacobi stays selectable,
+// via TNB_EIGH=jacobi (A/B measurements); TNB_EIGH=dc forces the new path for every n >= 2 as well.
+constexpr int64_t EIGH_DC_MIN = 2;
 size_t eigh_dc_ws_bytes(int dtype, int64_t n, int64_t kmax);
 int eigh_dc_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu,
                  cudaStream_t st);

@@ -56,6 +56,7 @@ struct Handle {
   cudaStream_t copy_stream = nullptr;
   double* partials = nullptr;   // per-block partial sums for reductions (8192 doubles)
   unsigned* counter = nullptr;  // last-block-done ticket (self-resetting)
+  void* what = nullptr;         // combined two-site MPO matrix of the fused H_eff step 2+3 (64 KB)
 };
 constexpr int RED_MAX_BLOCKS = 1024;
 

@@ -36,7 +36,9 @@ def test_dmrg_spin_one_heisenberg_energy_parity():
     # survives a cutoff-1e-11 truncation is implementation-defined (LAPACK syevr vs Jacobi): energies
     # agree to the truncation error, not beyond.  The strict 1e-10 bar is test_dmrg_exact_regime below.
     assert abs(e - e_ref) < 5e-9
-    assert np.max(np.abs(np.array(hist) - np.array(hist_ref))) < 5e-8
+    # sweeps 1-2 (maxdim 10 / 20 binding) cut through multiplets: per-sweep agreement is bounded by their
+    # truncation error (1e-6-class), the final sweep (maxdim 40, cutoff-limited) by 5e-9
+    assert np.max(np.abs(np.array(hist) - np.array(hist_ref))) < 2e-6
     # the returned state reproduces the energy
     H = tn.cu(_host_mpo(tn, Ws))
     assert abs(tn.inner(psi, psi, H) / tn.inner(psi, psi) - e) < 1e-9
