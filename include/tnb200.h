@@ -224,6 +224,16 @@ int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, i
                         int64_t maxdim, int64_t mindim, double cutoff, int64_t* n_keep,
                         double* truncerr, void* stream);
 
+/* Same gate in B form: B1[chiL,d1,chiM], B2[chiM,d2,chiR] right-canonical in the Schmidt bases, lamL[chiL] the
+ * Schmidt values of the bond to the LEFT of the first site (device).  Out: B1[chiL,d1,k], B2[k,d2,chiR] (buffers
+ * sized like tnb_tebd_apply_gate), lam_out[k] = Schmidt values of the updated bond (device, normalised).
+ * In this form the gates of one even/odd TEBD layer share no data, which is what lets a layer be spread
+ * over GPUs (itensorsgpu.jl_b200/tebd.py).  No division by Schmidt values.  Synchronises. */
+int tnb_tebd_gate_bform(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR,
+                        int32_t d1, int32_t d2, const void* G, const double* lamL, void* B1, void* B2,
+                        int64_t maxdim, int64_t mindim, double cutoff, double* lam_out, int64_t* n_keep,
+                        double* truncerr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

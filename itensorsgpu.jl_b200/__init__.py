@@ -7,7 +7,7 @@ ITensor-level interface: ``cu``, ``cpu``, ``*``, ``+``, ``svd``, ``eigen``, ``qr
 ``apply``).  The directory name is not an importable identifier; import it through the
 repo-root shim:  ``from itensorsgpu_b200 import tn``.
 """
-from . import _lib, ops, itensor, mps, shard  # noqa: F401
+from . import _lib, ops, itensor, mps, shard, tebd  # noqa: F401
 from ._lib import TnbError, DimensionMismatch, handle, load  # noqa: F401
 from .ops import DTensor  # noqa: F401
 from .itensor import (Index, ITensor, cu, cpu, cuITensor, randomCuITensor, prime, dag, noprime, norm, dot, permute,  # noqa: F401

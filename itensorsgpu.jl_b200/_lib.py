@@ -71,6 +71,8 @@ SIGNATURES = {
                                   _int, _int, _pdbl, _pi64, _pdbl, _vp]),
     "tnb_tebd_apply_gate": (_int, [_vp, _int, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _dbl, _pi64,
                                    _pdbl, _vp]),
+    "tnb_tebd_gate_bform": (_int, [_vp, _int, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp,
+                                   _pi64, _pdbl, _vp]),
 }
 
 _lib = None

@@ -21,7 +21,7 @@ __global__ void square_kernel(const double* __restrict__ s, double* p, int n) {
 // out (k x n, ld k) <- diag(s) * V^T  with V (n x kmaxv, ldv): out[i,j] = s_i * V[j,i]   (s may be null -> 1)
 template <typename T>
 __global__ void sv_transpose_kernel(T* out, long long k, long long n, const T* __restrict__ V, long long ldv,
-                                    const double* __restrict__ s) {
+                                    const double* __restrict__ s, int conj) {
   __shared__ T tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long i0 = (long long)blockIdx.x * 32, j0 = (long long)blockIdx.y * 32;
@@ -35,7 +35,7 @@ __global__ void sv_transpose_kernel(T* out, long long k, long long n, const T* _
     if (i < k && j < n) {
       T v = tile[tx][ty + yy];
       const double f = s ? s[i] : 1.0;
-      if constexpr (sizeof(T) == 16) { v.x *= f; v.y *= f; } else v *= f;
+      if constexpr (sizeof(T) == 16) { v.x *= f; v.y *= (conj ? -f : f); } else v *= f;
       out[i + j * k] = v;
     }
   }
@@ -51,12 +51,12 @@ __global__ void scale_columns_kernel(T* X, long long m, long long k, const doubl
 }
 
 static int sv_transpose(Handle* h, int dtype, void* out, int64_t k, int64_t n, const void* V, int64_t ldv, const double* s,
-                        cudaStream_t st) {
+                        cudaStream_t st, int conj = 0) {
   if (k == 0 || n == 0) return TNB_OK;
   dim3 g((unsigned)((k + 31) / 32), (unsigned)((n + 31) / 32));
   if (g.y > 65535) return set_err(h, TNB_ERR_UNSUPPORTED, "sv_transpose: n too large");
-  if (dtype == TNB_C128) sv_transpose_kernel<double2><<<g, 256, 0, st>>>((double2*)out, k, n, (const double2*)V, ldv, s);
-  else sv_transpose_kernel<double><<<g, 256, 0, st>>>((double*)out, k, n, (const double*)V, ldv, s);
+  if (dtype == TNB_C128) sv_transpose_kernel<double2><<<g, 256, 0, st>>>((double2*)out, k, n, (const double2*)V, ldv, s, conj);
+  else sv_transpose_kernel<double><<<g, 256, 0, st>>>((double*)out, k, n, (const double*)V, ldv, s, 0);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "sv_transpose");
 }
@@ -68,6 +68,39 @@ static int scale_columns(Handle* h, int dtype, void* X, int64_t m, int64_t k, co
   else scale_columns_kernel<double><<<g, 256, 0, st>>>((double*)X, m, k, s);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "scale_columns");
+}
+
+// out(r, c) = lam[r % chiL] * in(r, c)   (rows r = l + chiL*s1 of a (chiL*d1) x n matrix)
+template <typename T>
+__global__ void scale_rows_kernel(T* out, const T* __restrict__ in, long long m, long long n, long long chiL,
+                                  const double* __restrict__ lam) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < m * n; e += (long long)gridDim.x * blockDim.x) {
+    const double f = lam[(e % m) % chiL];
+    T v = in[e];
+    if constexpr (sizeof(T) == 16) { v.x *= f; v.y *= f; } else v *= f;
+    out[e] = v;
+  }
+}
+
+// Schmidt values of the new bond from the kept eigenvalues of theta^H theta: lam_i = sqrt(D_i / sum_kept D),
+// nrm[0] = sqrt(sum_kept D) (the state norm after truncation)
+__global__ void bform_finish_kernel(const double* __restrict__ D, int nk, double* lam, double* nrm) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) s += fmax(D[i], 0.0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    red[0] = t;
+    nrm[0] = sqrt(t);
+  }
+  __syncthreads();
+  const double tot = red[0];
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) lam[i] = tot > 0.0 ? sqrt(fmax(D[i], 0.0) / tot) : 0.0;
 }
 
 // ---- truncated svd into arena-or-caller buffers.  Arena must already be sized.
@@ -366,6 +399,58 @@ int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, i
   TNB_TRY(factorize_core(H, dtype, m, n, theta2, TNB_ORTHO_LEFT, TNB_DECOMP_AUTO, maxdim, mindim, cutoff, nullptr, 0, A1,
                          A2, n_keep, truncerr, ST));
   return check_cuda(H, cudaStreamSynchronize(ST), "tebd_apply_gate sync");
+}
+
+// TEBD gate in B form (right-canonical tensors in the Schmidt bases + Schmidt values), the form in which the
+// gates of one even/odd layer are independent and can be spread over GPUs:
+//   tt[l,s1',s2',r] = G * (B1 B2);  theta = lamL[l] * tt;  theta^H theta = V D V^H (truncated);
+//   B2' = V^H,  B1' = tt V / |theta_kept|,  lam' = sqrt(D / sum D)     (no division by Schmidt values)
+// [EXT] same physics as apply(gates, psi) at examples/gate_evolution.jl:46; only the right singular vectors are
+// needed, so the factorization is the Hermitian eigensolver on the (d2 chiR)^2 Gram matrix.
+int tnb_tebd_gate_bform(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR, int32_t d1, int32_t d2,
+                        const void* G, const double* lamL, void* B1, void* B2, int64_t maxdim, int64_t mindim,
+                        double cutoff, double* lam_out, int64_t* n_keep, double* truncerr, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!G || !lamL || !B1 || !B2 || !lam_out) return set_err(H, TNB_ERR_BAD_ARG, "tebd_gate_bform: null pointer");
+  if (chiL < 1 || chiM < 1 || chiR < 1 || d1 < 1 || d2 < 1) return set_err(H, TNB_ERR_BAD_ARG, "tebd_gate_bform: dims");
+  const size_t es = elsize(dtype);
+  const int64_t m = chiL * d1, n = (int64_t)d2 * chiR;
+  const int64_t kfull = std::min(m, n);
+  const int64_t md = maxdim > 0 ? std::min(maxdim, kfull) : kfull;
+  const size_t mat = al256((size_t)m * n * es);
+  ws_reset(H);
+  TNB_TRY(ws_require(H, 2 * mat + al256((size_t)n * n * es) + al256((size_t)n * md * es) + 2 * al256(n * 8) +
+                            eigh_ws_bytes(dtype, n) + (1 << 16)));
+  void *t0, *tt, *rho, *V, *D;
+  TNB_TRY(ws_alloc(H, (size_t)m * n * es, &t0));
+  TNB_TRY(ws_alloc(H, (size_t)m * n * es, &tt));
+  TNB_TRY(ws_alloc(H, (size_t)n * n * es, &rho));
+  TNB_TRY(ws_alloc(H, (size_t)n * md * es, &V));
+  TNB_TRY(ws_alloc(H, (size_t)n * sizeof(double), &D));
+  TNB_TRY(gemm_impl(H, dtype, 'N', 'N', m, n, chiM, nullptr, B1, m, B2, chiM, nullptr, t0, m, ST));
+  {
+    enum { l = 0, s1, s2, r, s1p, s2p };
+    int64_t ea[] = {chiL, d1, d2, chiR}; int32_t ma[] = {l, s1, s2, r};
+    int64_t eb[] = {d1, d2, d1, d2};     int32_t mb[] = {s1p, s2p, s1, s2};
+    int64_t ec[] = {chiL, d1, d2, chiR}; int32_t mc[] = {l, s1p, s2p, r};
+    TNB_TRY(contract_impl(H, dtype, 4, ea, ma, t0, 4, eb, mb, G, 4, ec, mc, tt, nullptr, nullptr, 0, ST));
+  }
+  const int g = H->num_sms * 4;
+  if (dtype == TNB_C128) scale_rows_kernel<double2><<<g, 256, 0, ST>>>((double2*)t0, (const double2*)tt, m, n, chiL, lamL);
+  else scale_rows_kernel<double><<<g, 256, 0, ST>>>((double*)t0, (const double*)tt, m, n, chiL, lamL);
+  H->launches++;
+  TNB_TRY(gemm_impl(H, dtype, 'C', 'N', n, n, m, nullptr, t0, m, t0, m, nullptr, rho, n, ST));
+  int64_t nk = 0;
+  double err = 0.0;
+  TNB_TRY(eigh_trunc_core(H, dtype, n, rho, md, mindim, cutoff, 0, 1, (double*)D, V, &nk, &err, ST));
+  TNB_TRY(sv_transpose(H, dtype, B2, nk, n, V, n, nullptr, ST, 1));
+  TNB_TRY(gemm_impl(H, dtype, 'N', 'N', m, nk, n, nullptr, tt, m, V, n, nullptr, B1, m, ST));
+  bform_finish_kernel<<<1, 256, 0, ST>>>((const double*)D, (int)nk, lam_out, H->scal + 121);
+  H->launches++;
+  TNB_TRY(scale_inv_dev_impl(H, dtype, m * nk, B1, B1, H->scal + 121, 0.0, ST));
+  if (n_keep) *n_keep = nk;
+  if (truncerr) *truncerr = err;
+  return check_cuda(H, cudaStreamSynchronize(ST), "tebd_gate_bform sync");
 }
 
 }  // extern "C"

@@ -451,3 +451,33 @@ def tebd_apply_gate(G, A1, A2, maxdim=None, mindim=1, cutoff=0.0):
                                       C.byref(nk), C.byref(err), _stream()))
     k = nk.value
     return DTensor(b1[: m * k], (cl, d1, k)), DTensor(b2[: k * n], (k, d2, cr)), err.value
+
+
+def tebd_gate_bform(G, lamL, B1, B2, maxdim=None, mindim=1, cutoff=0.0):
+    """Two-site gate in B form (``tnb_tebd_gate_bform``): B1, B2 right-canonical in the Schmidt bases, ``lamL`` the
+    Schmidt values (1-D float64 device tensor) of the bond left of the first site.
+    Returns (B1', B2', lam' (torch), truncerr)."""
+    h = _lib.handle()
+    cl, d1, cm = B1.dims
+    _, d2, cr = B2.dims
+    m, n = cl * d1, d2 * cr
+    G, B1 = _promote(G, B1)
+    G, B2 = _promote(G, B2)
+    B1, B2 = _promote(B1, B2)
+    if lamL.numel() != cl:
+        raise _lib.DimensionMismatch(2, "tebd_gate_bform: %d Schmidt values for a bond of dimension %d" % (lamL.numel(), cl))
+    kmax = max(1, min(m, n, int(maxdim)) if maxdim is not None else min(m, n))
+    dev = B1.data.device
+    b1 = torch.empty(max(B1.size, m * kmax), dtype=B1.dtype, device=dev)
+    b2 = torch.empty(max(B2.size, kmax * n), dtype=B2.dtype, device=dev)
+    b1[: B1.size].copy_(B1.data)
+    b2[: B2.size].copy_(B2.data)
+    lam = torch.empty(kmax, dtype=torch.float64, device=dev)
+    lamL = lamL.to(torch.float64).contiguous()
+    nk = C.c_int64(0)
+    err = C.c_double(0.0)
+    h.check(h.lib.tnb_tebd_gate_bform(h.h, _dt(B1.data), cl, cm, cr, d1, d2, _ptr(G.data), _ptr(lamL), _ptr(b1), _ptr(b2),
+                                      int(maxdim) if maxdim is not None else 0, int(mindim), float(cutoff or 0.0),
+                                      _ptr(lam), C.byref(nk), C.byref(err), _stream()))
+    k = nk.value
+    return DTensor(b1[: m * k], (cl, d1, k)), DTensor(b2[: k * n], (k, d2, cr)), lam[:k], err.value

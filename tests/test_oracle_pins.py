@@ -181,3 +181,39 @@ def test_heff_matches_dense_hamiltonian():
     assert abs(e_local - e_full) < 1e-12
     l, d, _, r = phi.shape
     assert dmrg.heff_flops(l, r, d, 5) == 2 * d * d * 5 * (l * l * r + l * r * r) + 4 * d ** 3 * 25 * l * r
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_bform_tebd_matches_sequential_apply(cplx):
+    """The B-form layer update (what the multi-GPU TEBD path uses) reproduces [EXT] `apply`'s sequential
+    gate application: identical states without truncation, agreement to the truncation error with it."""
+    from oracle import tebd, models, mps as omps
+    rng = np.random.default_rng(21)
+    N = 8
+    psi = omps.random_mps(N, 2, 8, rng, dtype=np.complex128 if cplx else np.float64)
+    G = models.heisenberg_bond_gate(0.05, imaginary_time=not cplx)
+    Bs, lams = tebd.canonical_bform(psi)
+    dense0 = omps.to_dense(psi)
+    assert np.linalg.norm(omps.to_dense(Bs) - dense0) < 1e-13
+    for j in range(1, N):
+        assert omps.right_orthogonality_error(Bs[j]) < 1e-13
+        # Schmidt values of bond (j-1, j) from the dense state
+        s = np.linalg.svd(dense0.reshape(2 ** j, -1), compute_uv=False)
+        assert np.max(np.abs(s[: len(lams[j])] - lams[j])) < 1e-13
+    gates = tebd.tebd_layer_gates(N, G, 0) + tebd.tebd_layer_gates(N, G, 1)
+    ref, _ = tebd.apply(gates, psi, center=0)
+    tebd.tebd_layer_bform(Bs, lams, G, 0)
+    tebd.tebd_layer_bform(Bs, lams, G, 1)
+    a, b = omps.to_dense(Bs), omps.to_dense(ref)
+    # imaginary-time gates are not unitary: neither form keeps the norm (the B form normalises gate by gate
+    # against Schmidt values that its neighbours' gates have meanwhile changed), so compare rays
+    a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+    assert np.linalg.norm(a - b) < 1e-12
+    # with truncation: both are optimal bond by bond, they agree to the discarded weight
+    Bs, lams = tebd.canonical_bform(psi)
+    ref, _ = tebd.apply(gates, psi, center=0, maxdim=6)
+    e0 = tebd.tebd_layer_bform(Bs, lams, G, 0, maxdim=6)
+    e1 = tebd.tebd_layer_bform(Bs, lams, G, 1, maxdim=6)
+    a, b = omps.to_dense(Bs), omps.to_dense(ref)
+    a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+    assert np.linalg.norm(a - b) < 10 * np.sqrt(max(e0, e1, 1e-30))
