@@ -86,13 +86,15 @@ struct TileGeom {
   static constexpr int ELEMS = ELEMS_K > ELEMS_R ? ELEMS_K : ELEMS_R;
 };
 
-// cp.async staging of one operand tile.  Per thread: `rowoff[]` = element offsets of the tile
-// rows it copies (registers, decoded once per CTA; -1 = out of range).  Per K tile `begin()`
-// decodes the K offset(s) with integer ALU work only; `issue(pass)` is then one select, one
-// 64-bit add and one LDGSTS.  The kernel issues the passes inside the LAST k-step of the tile
-// being computed: LDGSTS share the MIO queue with the fragment LDS, and a copy burst placed
-// before the tile's fragment loads delays them and starves the DMMA pipe (measured: 30.9 vs
-// 34+ TFLOP/s).
+// cp.async staging of one operand tile.  Everything a copy needs is kept as running state so that the inner
+// loop pays ONE 64-bit add + one LDGSTS per 16-byte copy (ncu, round 1: with offsets re-derived per copy the
+// kernel executed as many IMADs as DMMAs and the resulting fixed-latency stalls held the DMMA pipe at 82-89%):
+//   rowptr[]  global byte address of each tile row this thread copies (decoded once per CTA)
+//   kb[]      byte offset of this thread's k (per k-row for the free-major form); advanced by BK * stride of the
+//             leading K mode per tile, re-decoded only when the leading mode wraps (once per ext0/BK tiles)
+//   dst[]     shared-memory byte offset inside a stage (constant)
+// The kernel issues the passes inside the LAST k-step of the tile being computed: LDGSTS share the MIO queue
+// with the fragment LDS, and a copy burst placed before the tile's fragment loads delays them.
 template <bool CPLX, bool CONTIG_K, int VEC, int ROWS, int BK, int NT, bool KY>
 struct Loader {
   using G = TileGeom<CPLX, ROWS, BK>;
@@ -107,51 +109,72 @@ struct Loader {
   static_assert(NT % (CONTIG_K ? VPR : VPK) == 0, "thread mapping");
   static_assert(NPASS >= 1, "tile too small for the CTA");
 
-  long long rowoff[NROW];
-  long long koff[NKO];   // -1 = k out of range
+  const char* rowptr[NROW];
+  bool rowok[NROW];
+  long long kb[NKO];     // byte offset of k
+  int kabs[NKO];         // absolute k of this thread (pass)
+  int kpos[NKO];         // position inside the leading K mode
+  bool kok[NKO];
+  unsigned dst[NPASS];
+  long long kstep;       // BK * stride(leading K mode) * EB
+  int kext0;
 
-  __device__ __forceinline__ void init(const Group& g, int row0, int R, int tid) {
+  __device__ __forceinline__ void init(const Group& g, const Group& gk, const char* base, int row0, int R, int K, int tid) {
     if (CONTIG_K) {
 #pragma unroll
       for (int i = 0; i < NPASS; ++i) {
-        const int r = row0 + tid / VPR + i * RPP;
-        rowoff[i] = (r < R) ? decode<false>(g, r) : -1;
+        const int rl = tid / VPR + i * RPP;
+        const int r = row0 + rl;
+        rowok[i] = r < R;
+        rowptr[i] = base + (rowok[i] ? decode<false>(g, r) * EB : 0);
+        dst[i] = (unsigned)((rl * G::PK + (tid % VPR) * VEC) * EB);
       }
+      kabs[0] = (tid % VPR) * VEC;
     } else {
       const int r = row0 + (tid % VPK) * VEC;
-      rowoff[0] = (r < R) ? decode<false>(g, r) : -1;
+      rowok[0] = r < R;
+      rowptr[0] = base + (rowok[0] ? decode<false>(g, r) * EB : 0);
+#pragma unroll
+      for (int i = 0; i < NPASS; ++i) {
+        const int kl = tid / VPK + i * KPP;
+        kabs[i] = kl;
+        dst[i] = (unsigned)((kl * G::PR + (tid % VPK) * VEC) * EB);
+      }
+    }
+    kext0 = gk.ext[0];
+    kstep = (long long)BK * (KY ? gk.sY[0] : gk.sX[0]) * EB;
+#pragma unroll
+    for (int i = 0; i < NKO; ++i) {
+      kok[i] = kabs[i] < K;
+      kb[i] = kok[i] ? decode<KY>(gk, kabs[i]) * EB : 0;
+      kpos[i] = kabs[i] % kext0;
     }
   }
 
-  __device__ __forceinline__ void begin(const Group& gk, int k0, int K, int tid) {
-    if (CONTIG_K) {
-      const int k = k0 + (tid % VPR) * VEC;
-      koff[0] = (k < K) ? decode<KY>(gk, k) : -1;
-    } else {
+  // move this thread's k forward by one tile (called once per tile, after the tile's copies were issued)
+  __device__ __forceinline__ void advance(const Group& gk, int K) {
 #pragma unroll
-      for (int i = 0; i < NPASS; ++i) {
-        const int k = k0 + tid / VPK + i * KPP;
-        koff[i] = (k < K) ? decode<KY>(gk, k) : -1;
+    for (int i = 0; i < NKO; ++i) {
+      kabs[i] += BK;
+      kpos[i] += BK;
+      kok[i] = kabs[i] < K;
+      if (kpos[i] >= kext0) {                   // leading K mode wrapped: re-decode (rare)
+        kb[i] = kok[i] ? decode<KY>(gk, kabs[i]) * EB : 0;
+        kpos[i] = kabs[i] % kext0;
+      } else {
+        kb[i] += kstep;
       }
     }
   }
 
-  __device__ __forceinline__ void issue(int pass, const char* base, char* smem, int tid) const {
-    if (CONTIG_K) {
-      const int kv = (tid % VPR) * VEC;
-      const int r = tid / VPR + pass * RPP;
-      char* dst = smem + (size_t)(r * G::PK + kv) * EB;
-      const bool ok = (koff[0] >= 0) && (rowoff[pass] >= 0);
-      const char* src = base + (ok ? (rowoff[pass] + koff[0]) * EB : 0);
-      if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
-    } else {
-      const int rv = (tid % VPK) * VEC;
-      const int kl = tid / VPK + pass * KPP;
-      char* dst = smem + (size_t)(kl * G::PR + rv) * EB;
-      const bool ok = (rowoff[0] >= 0) && (koff[pass] >= 0);
-      const char* src = base + (ok ? (rowoff[0] + koff[pass]) * EB : 0);
-      if (VEC * EB == 16) cp_async16(dst, src, ok); else cp_async8(dst, src, ok);
-    }
+  __device__ __forceinline__ void issue(int pass, unsigned stage_smem) const {
+    const int ri = CONTIG_K ? pass : 0, ki = CONTIG_K ? 0 : pass;
+    const bool ok = rowok[ri] && kok[ki];
+    const char* src = rowptr[ri] + (ok ? kb[ki] : 0);
+    const unsigned d = stage_smem + dst[pass];
+    const int sz = ok ? VEC * EB : 0;
+    if (VEC * EB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(sz));
   }
 };
 
@@ -193,8 +216,6 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
   using LB = Loader<CPLX, BKM, VB, BN, BK, NT, true>;
   LA la;
   LB lb;
-  la.init(p.gm, m0, p.M, tid);
-  lb.init(p.gn, n0, p.N, tid);
 
   const char* Ab = (const char*)p.A;
   const char* Bb = (const char*)p.B;
@@ -206,6 +227,9 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
     Cb += (p.boffC ? p.boffC[bz] : bz * p.bstrideC) * EB;
   }
   const int KT = (p.K + BK - 1) / BK;
+  la.init(p.gm, p.gk, Ab, m0, p.M, p.K, tid);
+  lb.init(p.gn, p.gk, Bb, n0, p.N, p.K, tid);
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
 
   double acc[MI][NI][CPLX ? 4 : 2];
 #pragma unroll
@@ -219,12 +243,12 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
 #pragma unroll
   for (int s = 0; s < ST - 1; ++s) {
     if (s < KT) {
-      la.begin(p.gk, s * BK, p.K, tid);
-      lb.begin(p.gk, s * BK, p.K, tid);
 #pragma unroll
-      for (int c = 0; c < LA::NPASS; ++c) la.issue(c, Ab, (char*)smem + s * STAGE_BYTES, tid);
+      for (int c = 0; c < LA::NPASS; ++c) la.issue(c, smem_u32 + s * STAGE_BYTES);
 #pragma unroll
-      for (int c = 0; c < LB::NPASS; ++c) lb.issue(c, Bb, (char*)smem + s * STAGE_BYTES + A_BYTES, tid);
+      for (int c = 0; c < LB::NPASS; ++c) lb.issue(c, smem_u32 + s * STAGE_BYTES + A_BYTES);
+      la.advance(p.gk, p.K);
+      lb.advance(p.gk, p.K);
     }
     cp_async_commit();
   }
@@ -237,15 +261,14 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
     if (DBG != 3) { cp_async_wait<ST - 2>(); __syncthreads(); }
     const int nk = kt + ST - 1;
     const bool more = (DBG == 1 || DBG == 3) ? false : nk < KT;
-    char* nsA = (char*)smem + (nk % ST) * STAGE_BYTES;
-    char* nsB = nsA + A_BYTES;
+    const unsigned nsA = smem_u32 + (nk % ST) * STAGE_BYTES;
+    const unsigned nsB = nsA + A_BYTES;
     const unsigned char* sA = smem + (kt % ST) * STAGE_BYTES;
     const unsigned char* sB = sA + A_BYTES;
     // copy pass c of the tile ST-1 ahead (A passes first, then B)
-    if (more) { la.begin(p.gk, nk * BK, p.K, tid); lb.begin(p.gk, nk * BK, p.K, tid); }
     auto copy_pass = [&](int c) {
-      if (c < LA::NPASS) la.issue(c, Ab, nsA, tid);
-      else lb.issue(c - LA::NPASS, Bb, nsB, tid);
+      if (c < LA::NPASS) la.issue(c, nsA);
+      else lb.issue(c - LA::NPASS, nsB);
     };
     if (!CPLX) {
       const double* As = (const double*)sA;
@@ -331,6 +354,7 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
         }
       }
     }
+    if (more) { la.advance(p.gk, p.K); lb.advance(p.gk, p.K); }
     cp_async_commit();
   }
   cp_async_wait<0>();

@@ -16,6 +16,7 @@
 #include "tnb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace tnb {
 
@@ -334,6 +335,155 @@ __global__ void __launch_bounds__(TD_K2T, 2) td_k2_kernel(const typename ElemT<C
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Symmetric form of K2 for large trailing matrices: read only the LOWER triangle (half the HBM traffic).
+// The trailing matrix is cut into 128 x 128 tiles; tile (I,J), I >= J, is read once by one CTA and serves both
+// y_I += A_IJ v_J (row part, accumulated per lane, then across the 8 warps in a fixed order) and
+// y_J += A_IJ^H v_I (column dots).  Each (block, tile) pair owns one slot of P, so there are no atomics and the
+// result is bit-reproducible; K2R sums the slots of every block in a fixed order.
+// ------------------------------------------------------------------------------------
+constexpr int TD_TS = 128;
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return ld_stream16(p); }
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) td_k2s_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i, int j,
+                                                      typename ElemT<CPLX>::T* ZL, typename ElemT<CPLX>::T* ZR, long long ldz,
+                                                      const typename ElemT<CPLX>::T* __restrict__ scal,
+                                                      typename ElemT<CPLX>::T* __restrict__ P, int nbt, int ntiles,
+                                                      typename ElemT<CPLX>::T* __restrict__ ybuf) {
+  using T = typename ElemT<CPLX>::T;
+  constexpr int nb = TD_NB, TS = TD_TS;
+  __shared__ T vI[TS], vJ[TS], colres[TS];
+  __shared__ T rowacc[8][TS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long r0 = i + 1;
+  const int nt = (int)(n - r0);
+  const T sc = scal[0];
+  const T* x = A + r0 + (size_t)i * n;
+  auto vat = [&](int g) -> T { return g >= nt ? a_zero<T>() : (g == 0 ? a_one<T>() : a_mul(__ldg(x + g), sc)); };
+  if ((int)blockIdx.x >= ntiles) {
+    // panel dots q = V^H v, p = W^H v: one warp per panel column
+    const int pc = ((int)blockIdx.x - ntiles) * 8 + warp;
+    if (pc >= 2 * j) return;
+    const T* col = (pc < j) ? ZL + r0 + (size_t)pc * ldz : ZL + r0 + (size_t)(nb + pc - j) * ldz;
+    T acc = a_zero<T>();
+    int t = lane;
+    for (; t + 96 < nt; t += 128) {
+      T cv[4], vv[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { cv[w] = col[t + 32 * w]; vv[w] = __ldg(x + t + 32 * w); }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) acc = a_add(acc, a_cmul(cv[w], (t + 32 * w == 0) ? a_one<T>() : a_mul(vv[w], sc)));
+    }
+    for (; t < nt; t += 32) acc = a_add(acc, a_cmul(col[t], vat(t)));
+    acc = a_warp_sum(acc);
+    if (lane == 0) ybuf[nt + pc] = acc;
+    return;
+  }
+  int I = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((I + 1) * (I + 2) / 2 <= (int)blockIdx.x) ++I;
+  while (I * (I + 1) / 2 > (int)blockIdx.x) --I;
+  const int J = (int)blockIdx.x - I * (I + 1) / 2;
+  const bool diag = (I == J);
+  if (tid < TS) {
+    const T v = vat(I * TS + tid);
+    vI[tid] = v;
+    if (diag && I * TS + tid < nt) {
+      ZL[r0 + I * TS + tid + (size_t)j * ldz] = v;
+      ZR[r0 + I * TS + tid + (size_t)(nb + j) * ldz] = v;
+    }
+  } else {
+    vJ[tid - TS] = vat(J * TS + tid - TS);
+  }
+  __syncthreads();
+  T vr[4], yr[4];
+  bool rok[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { vr[q] = vI[lane + 32 * q]; yr[q] = a_zero<T>(); rok[q] = (I * TS + lane + 32 * q) < nt; }
+  const T* base = A + (r0 + (size_t)I * TS + lane) + (size_t)(r0 + (size_t)J * TS) * n;
+#pragma unroll 1
+  for (int cb = 0; cb < TS / 8; cb += 8) {
+    T av[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = warp + 8 * (cb + u);
+      const bool cok = (J * TS + c) < nt;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        bool ok = cok && rok[q];
+        if (diag) ok = ok && (lane + 32 * q >= c);
+        av[u][q] = ok ? ld_stream(base + 32 * q + (size_t)c * n) : a_zero<T>();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = warp + 8 * (cb + u);
+      const T vc = vJ[c];
+      T s = a_zero<T>();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        s = a_add(s, a_cmul(av[u][q], vr[q]));
+        if (!diag || (lane + 32 * q > c)) yr[q] = a_add(yr[q], a_mul(av[u][q], vc));
+      }
+      s = a_warp_sum(s);
+      if (lane == 0) colres[c] = s;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) rowacc[warp][lane + 32 * q] = yr[q];
+  __syncthreads();
+  if (tid < TS) {
+    T rs = a_zero<T>();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) rs = a_add(rs, rowacc[w][tid]);
+    if (diag) P[((size_t)I * nbt + I) * TS + tid] = a_add(rs, colres[tid]);
+    else {
+      P[((size_t)I * nbt + J) * TS + tid] = rs;
+      P[((size_t)J * nbt + I) * TS + tid] = colres[tid];
+    }
+  }
+}
+
+// y[t] = sum_k P[block(t)][k][t % TS]; also this CTA's share of y^H v
+template <bool CPLX>
+__global__ void __launch_bounds__(256) td_k2r_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i,
+                                                      const typename ElemT<CPLX>::T* __restrict__ scal,
+                                                      const typename ElemT<CPLX>::T* __restrict__ P, int nbt,
+                                                      typename ElemT<CPLX>::T* __restrict__ ybuf,
+                                                      typename ElemT<CPLX>::T* __restrict__ yparts) {
+  using T = typename ElemT<CPLX>::T;
+  constexpr int TS = TD_TS;
+  __shared__ T wsum[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long r0 = i + 1;
+  const int nt = (int)(n - r0);
+  const int t = blockIdx.x * 256 + tid;
+  T yv = a_zero<T>();
+  if (t < nt) {
+    const T* src = P + ((size_t)(t / TS) * nbt) * TS + (t % TS);
+    T y = a_zero<T>();
+#pragma unroll 8
+    for (int k = 0; k < nbt; ++k) y = a_add(y, src[(size_t)k * TS]);
+    ybuf[t] = y;
+    const T v = (t == 0) ? a_one<T>() : a_mul(A[r0 + t + (size_t)i * n], scal[0]);
+    yv = a_cmul(y, v);
+  }
+  yv = a_warp_sum(yv);
+  if (lane == 0) wsum[warp] = yv;
+  __syncthreads();
+  if (tid == 0) {
+    T s = a_zero<T>();
+    for (int w = 0; w < 8; ++w) s = a_add(s, wsum[w]);
+    yparts[blockIdx.x] = s;
+  }
+}
+
 // zero the part of A above the reflectors: column c keeps rows > c (pivot c+1 holds the explicit 1);
 // the last column holds no reflector.
 template <typename T>
@@ -346,7 +496,9 @@ __global__ void td_clean_kernel(T* A, long long n) {
 
 size_t tridiag_ws_bytes(int dtype, int64_t n) {
   const size_t es = elsize(dtype);
-  return 2 * al256((size_t)n * 2 * TD_NB * es) + al256((size_t)(n + 2 * TD_NB) * es) + al256(64) + al256(1024 * es) + 4096;
+  const size_t nbt = (size_t)(n + TD_TS - 1) / TD_TS;
+  return 2 * al256((size_t)n * 2 * TD_NB * es) + al256((size_t)(n + 2 * TD_NB) * es) + al256(64) + al256(1024 * es) +
+         al256(nbt * nbt * TD_TS * es) + al256((n / 256 + 2) * es) + 4096;
 }
 
 template <bool CPLX, int CW>
@@ -380,9 +532,18 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
   TNB_TRY(ws_alloc(h, (size_t)n * 2 * nb * sizeof(T), &ZRv));
   TNB_TRY(ws_alloc(h, (size_t)(n + 2 * nb) * sizeof(T), &yv));
   TNB_TRY(ws_alloc(h, 64, &scv));
-  TNB_TRY(ws_alloc(h, (size_t)h->num_sms * 4 * sizeof(T), &ypv));
+  TNB_TRY(ws_alloc(h, (size_t)std::max<int64_t>(h->num_sms * 4, n / 256 + 2) * sizeof(T), &ypv));
   T *ZL = (T*)ZLv, *ZR = (T*)ZRv, *ybuf = (T*)yv, *scal = (T*)scv, *yparts = (T*)ypv;
   int nparts = 0;
+  // symmetric (half-traffic) matvec for trailing sizes >= sym_min; TNB_TD_SYM_MIN overrides, 0 disables
+  const char* sm_env = getenv("TNB_TD_SYM_MIN");
+  const int64_t sym_min = sm_env ? atoll(sm_env) : 3072;
+  void* Pv = nullptr;
+  if (sym_min > 0 && n - 1 >= sym_min) {
+    const size_t nbt = (size_t)(n + TD_TS - 1) / TD_TS;
+    TNB_TRY(ws_alloc(h, nbt * nbt * TD_TS * sizeof(T), &Pv));
+  }
+  T* P = (T*)Pv;
   static bool attr_done = false;
   if (!attr_done) {
     TNB_CUDA(h, cudaFuncSetAttribute(td_k2_kernel<CPLX, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -406,7 +567,15 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
       const int64_t i = p0 + j;
       k1(i, j - 1, 1);
       const int Ct = (int)(n - i - 1) + 2 * j;
-      if (Ct >= 2 * 32 * h->num_sms) nparts = launch_k2<CPLX, 2>(h, A, n, i, j, ZL, ZR, n, scal, ybuf, yparts, st);
+      const int nt = (int)(n - i - 1);
+      if (P && nt >= sym_min) {
+        const int nbt = (nt + TD_TS - 1) / TD_TS;
+        const int ntiles = nbt * (nbt + 1) / 2;
+        td_k2s_kernel<CPLX><<<ntiles + (2 * j + 7) / 8, 256, 0, st>>>(A, n, i, j, ZL, ZR, n, scal, P, nbt, ntiles, ybuf);
+        nparts = (nt + 255) / 256;
+        td_k2r_kernel<CPLX><<<nparts, 256, 0, st>>>(A, n, i, scal, P, nbt, ybuf, yparts);
+        h->launches += 2;
+      } else if (Ct >= 2 * 32 * h->num_sms) nparts = launch_k2<CPLX, 2>(h, A, n, i, j, ZL, ZR, n, scal, ybuf, yparts, st);
       else nparts = launch_k2<CPLX, 1>(h, A, n, i, j, ZL, ZR, n, scal, ybuf, yparts, st);
     }
     const int64_t lo = p0 + jb;

@@ -37,7 +37,7 @@ def main():
     out = []
     which = sys.argv[1:] or ["gemm", "heff", "vec", "cplx"]
     if "gemm" in which:
-        for (m, n, k) in [(8192, 8192, 8192), (16384, 20480, 4096), (4096, 5120, 1024)]:
+        for (m, n, k) in [(8192, 8192, 8192), (16384, 20480, 4096), (16384, 4096, 20480), (4096, 5120, 1024)]:
             A = rnd(m * k).view(m, k)
             B = rnd(k * n).view(k, n)
             best, med = timeit(lambda: torch.matmul(A, B))
