@@ -260,9 +260,25 @@ def run_gpu(args):
         slab = tn.DTensor.empty((clp, D, D, chi))
         gathered = torch.empty(world * clp * D * D * chi, device="cuda", dtype=torch.float64)
 
-        def step():
+        def step_nccl():
             tn.ops.heff_apply_shard(L, W1, W2, R, phi, out=slab)
             dist.all_gather_into_tensor(gathered, slab.data)   # rank-major slabs == [r', s2', s1', G, l'_shard]
+
+        # default: the all-gather fused into the last GEMM (NVLink peer stores + device-side flag barrier);
+        # --gather nccl (or a peer-mapping failure, reported in config) uses library all-gather instead
+        fused = None
+        gather_mode = "nccl all-gather after the slab kernels"
+        if args.gather == "fused":
+            try:
+                fused = tn.shard.FusedShardedHeff(phi.dims, torch.float64)
+                gather_mode = "all-gather fused into the step-4 GEMM epilogue (NVLink peer stores, device flag barrier)"
+            except Exception as ex:   # noqa: BLE001
+                gather_mode = "nccl all-gather (peer mapping unavailable: %s)" % str(ex)[:80]
+        if fused is not None:
+            def step():
+                fused.apply(L, W1, W2, R, phi)
+        else:
+            step = step_nccl
 
     def barrier():
         if world > 1:
@@ -326,7 +342,8 @@ def run_gpu(args):
             phi.data.copy_(ph, non_blocking=True)
             step()
             if rank == 0:
-                oh.copy_(gathered, non_blocking=True)
+                oh.copy_(fused.outs[(fused.epoch - 1) % len(fused.outs)].local() if fused is not None else gathered,
+                         non_blocking=True)
             torch.cuda.synchronize()
     for _ in range(2):
         e2e_step()
@@ -370,7 +387,7 @@ def run_gpu(args):
             "config": {"workload": "C3 central-bond H_eff*phi (S=1/2 Heisenberg, N=100, maxdim 4096, d=2, w=5)",
                        "chi": chi, "d": D, "w": W, "flop_per_step": F,
                        "l2": "operands 0.5-2.7 GB per contraction, far larger than the 126 MB L2 (no flush needed)",
-                       "parallelism": "single GPU" if world == 1 else "output bond l' sharded x%d + NCCL all-gather" % world},
+                       "parallelism": "single GPU" if world == 1 else "output bond l' sharded x%d; %s" % (world, gather_mode)},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": traffic, "kernel": "contract_kernel<f64, A K-major, B K-major, 16-byte copies, Cfg<64x128x16, warp 32x64, 3 stages, 2 CTA/SM>> (H_eff steps 1 and 4)",
                          "flop_per_launch": flops_per_launch, "ms_per_launch": kern_s * 1e3, "peak_source": peak_src},
@@ -384,6 +401,9 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        if fused is not None:
+            fused.status()
+            fused.close()
         dist.destroy_process_group()
 
 
@@ -395,6 +415,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chi", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: how the slabs of H*phi reach every rank")
     ap.add_argument("--no-sweep", action="store_true", help="skip the DMRG sweep-seconds sample (metric M1)")
     ap.add_argument("--sweep-branch", default="svd", choices=["svd", "eigen"],
                     help="factorize rule of the sweep sample: svd = cutoff 0 / noise 0 (C3), eigen = cutoff 1e-11 / noise 1e-10")

@@ -168,6 +168,29 @@ int tnb_heff_apply(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const v
 int tnb_heff_apply_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int64_t lp_extent,
                          const void* L_slab, const void* W1, const void* W2, const void* R,
                          const void* phi, void* out_slab, void* stream);
+/* Sharded H_eff with the all-gather FUSED into the last contraction (one process per GPU, one NVSwitch node):
+ * the epilogue of step 4 stores this rank's slab of H*phi straight into the full-vector buffer
+ * out_peers[g] ([chiL,d1,d2,chiR], same layout as phi) of EVERY rank g through NVLink peer pointers, so the
+ * transfer overlaps the GEMM tile by tile and no reassembly pass is needed; a device-side barrier over the
+ * peer-mapped flag arrays flag_peers[g] (world uint64 each, zero-initialised) then makes all slabs visible to
+ * work queued behind this call on `stream`.  chiL = world * lp_extent.  `epoch` must increase by one with
+ * every call on the same buffers; alternate two out buffers if a peer may still read the previous result.
+ * out_peers / flag_peers are HOST arrays of `world` device pointers (own buffer included, from tnb_peer_alloc /
+ * tnb_peer_open).  Asynchronous.  (Replaces tnb_heff_apply_shard + ncclAllGather + the slab interleave.) */
+int tnb_heff_apply_shard_fused(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int rank, int world,
+                               int64_t lp_extent, const void* L_slab, const void* W1, const void* W2,
+                               const void* R, const void* phi, void* const* out_peers,
+                               void* const* flag_peers, uint64_t epoch, void* stream);
+/* Peer-mapped device buffers (CUDA IPC).  tnb_peer_alloc: zero-filled cudaMalloc + its 64-byte IPC handle (send it
+ * to the other ranks with any host-side transport); tnb_peer_open maps a peer's buffer into this process;
+ * tnb_peer_close unmaps it; tnb_peer_free releases an own buffer.  tnb_peer_status synchronises and reports
+ * whether a device-side peer barrier ever timed out (a rank that never arrived). */
+int tnb_peer_alloc(tnb_handle_t h, size_t bytes, void** ptr, unsigned char* ipc_handle_out /* 64 bytes */);
+int tnb_peer_open(tnb_handle_t h, const unsigned char* ipc_handle /* 64 bytes */, void** ptr);
+int tnb_peer_close(tnb_handle_t h, void* ptr);
+int tnb_peer_free(tnb_handle_t h, void* ptr);
+int tnb_peer_status(tnb_handle_t h, void* stream);
+
 /* Same, phi and out in HOST memory (pinned or pageable): H2D + apply + D2H, synchronous.
  * This is the end-to-end form timed by bench.py `e2e`. */
 int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,

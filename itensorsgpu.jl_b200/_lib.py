@@ -60,6 +60,13 @@ SIGNATURES = {
     "tnb_qr": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "tnb_heff_apply": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnb_heff_apply_shard": (_int, [_vp, _int, _pbd, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnb_heff_apply_shard_fused": (_int, [_vp, _int, _pbd, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp),
+                                          C.POINTER(_vp), C.c_uint64, _vp]),
+    "tnb_peer_alloc": (_int, [_vp, C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "tnb_peer_open": (_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "tnb_peer_close": (_int, [_vp, _vp]),
+    "tnb_peer_free": (_int, [_vp, _vp]),
+    "tnb_peer_status": (_int, [_vp, _vp]),
     "tnb_heff_apply_host": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnb_env_update_left": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tnb_env_update_right": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -383,22 +383,30 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
       for (int i = 0; i < MI; ++i) {
         if (!okm[i]) continue;
         if (!CPLX) {
-          double* c = (double*)Cb + offm[i] + offn;
           double v = p.alpha_re * acc[i][j][e];
-          if (has_beta) v += p.beta_re * (*c);
-          *c = v;
+          if (p.npeer > 0) {      // fused all-gather: same element to every GPU's buffer (NVLink peer stores)
+            for (int g = 0; g < p.npeer; ++g) ((double*)p.peerC[g])[offm[i] + offn] = v;
+          } else {
+            double* c = (double*)Cb + offm[i] + offn;
+            if (has_beta) v += p.beta_re * (*c);
+            *c = v;
+          }
         } else {
-          double2* c = (double2*)Cb + offm[i] + offn;
           const double xr = acc[i][j][e], xi = acc[i][j][2 + e];
           double2 v;
           v.x = p.alpha_re * xr - p.alpha_im * xi;
           v.y = p.alpha_re * xi + p.alpha_im * xr;
-          if (has_beta) {
-            const double2 o = *c;
-            v.x += p.beta_re * o.x - p.beta_im * o.y;
-            v.y += p.beta_re * o.y + p.beta_im * o.x;
+          if (p.npeer > 0) {
+            for (int g = 0; g < p.npeer; ++g) ((double2*)p.peerC[g])[offm[i] + offn] = v;
+          } else {
+            double2* c = (double2*)Cb + offm[i] + offn;
+            if (has_beta) {
+              const double2 o = *c;
+              v.x += p.beta_re * o.x - p.beta_im * o.y;
+              v.y += p.beta_re * o.y + p.beta_im * o.x;
+            }
+            *c = v;
           }
-          *c = v;
         }
       }
     }
@@ -571,6 +579,20 @@ int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32
                   const void* A, int nB, const int64_t* extB, const int32_t* modeB,
                   const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
                   const void* alpha, const void* beta, int flags, cudaStream_t st) {
+  return contract_impl_ex(h, dtype, nA, extA, modeA, A, nB, extB, modeB, B, nC, extC, modeC, C, alpha, beta, flags, st,
+                          nullptr, nullptr, 0);
+}
+
+// strideC (optional): element stride of every C mode (C is then a strided window of a larger tensor);
+// peerC/npeer (optional): the epilogue stores every output element to ALL npeer base pointers (peer-mapped
+// buffers of the other GPUs included) instead of C -- the all-gather of a sharded result fused into the GEMM.
+int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
+                     const void* A, int nB, const int64_t* extB, const int32_t* modeB,
+                     const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                     const void* alpha, const void* beta, int flags, cudaStream_t st,
+                     const int64_t* strideC, void* const* peerC, int npeer) {
+  if (npeer < 0 || npeer > TNB_MAX_PEERS) return set_err(h, TNB_ERR_BAD_ARG, "contract: npeer %d", npeer);
+  if (npeer > 0 && beta) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: beta with peer stores");
   if (dtype != TNB_F64 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: dtype %d", dtype);
   if (nA < 0 || nB < 0 || nC < 0 || nA > 64 || nB > 64 || nC > 64)
     return set_err(h, TNB_ERR_BAD_ARG, "contract: bad rank");
@@ -606,7 +628,7 @@ int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32
     ModeRec* r = find(modeC[i]);
     if (!r) return set_err(h, TNB_ERR_BAD_ARG, "contract: output mode %d is in neither input", modeC[i]);
     if (r->ext != extC[i]) return set_err(h, TNB_ERR_DIM_MISMATCH, "contract: mode %d has extent %lld in C", modeC[i], (long long)extC[i]);
-    r->sC = s; r->posC = i;
+    r->sC = strideC ? strideC[i] : s; r->posC = i;
     s *= extC[i];
   }
   std::vector<ModeRec> gm, gn, gk;
@@ -645,6 +667,8 @@ int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32
   set_scalars(p, dtype, alpha, beta);
   p.conjA = (flags & TNB_CONJ_A) ? 1 : 0;
   p.conjB = (flags & TNB_CONJ_B) ? 1 : 0;
+  p.npeer = npeer;
+  for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
   return launch_planned(h, dtype, p, st);
 }
 

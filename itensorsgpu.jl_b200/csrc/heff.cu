@@ -118,10 +118,27 @@ static size_t heff_ws_bytes(int dtype, const tnb_bond_dims* d) {
 // out <- (((phi*L)*W1)*W2)*R using two ping-pong temporaries t0,t1 (each base*max(w) elements)
 // `clp` = extent of the output bond l' held by this call: chiL normally, chiL/G when the
 // output bond is sharded over G GPUs (L is then the slab L[:, l'_shard, :]).
+struct PeerOut {           // fused all-gather of the sharded result (step 4 epilogue stores to every GPU)
+  int npeer = 0;
+  void* base[TNB_MAX_PEERS];   // full-vector buffers [chiL,d1,d2,chiR] of every rank, already offset to this rank's l' slab
+};
+
 static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* L, const void* W1,
                      const void* W2, const void* R, const void* phi, void* out, void* t0, void* t1,
-                     cudaStream_t st) {
+                     cudaStream_t st, const PeerOut* peers = nullptr) {
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
+  // step 4 writes out[l'_slab, s1', s2', r'] -- dense, or (fused gather) a strided window of the full vector
+  auto step4 = [&](const void* T3) -> int {
+    int64_t ea[] = {cr, clp, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t eb[] = {cr, cr, wr};          int32_t mb[] = {mR, mRp, mC};
+    int64_t ec[] = {clp, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
+    if (peers && peers->npeer > 0) {
+      int64_t sc[] = {1, cl, cl * d1, cl * d1 * d2};
+      return contract_impl_ex(h, dtype, 5, ea, ma, T3, 3, eb, mb, R, 4, ec, mc, peers->base[0], nullptr, nullptr, 0, st, sc,
+                              peers->base, peers->npeer);
+    }
+    return contract_impl(h, dtype, 5, ea, ma, T3, 3, eb, mb, R, 4, ec, mc, out, nullptr, nullptr, 0, st);
+  };
   {  // 1. T1[s1,s2,r,l',a] = phi[l,s1,s2,r] L[l,l',a]
     int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
     int64_t eb[] = {cl, clp, wl};    int32_t mb[] = {mL, mLp, mA};
@@ -130,11 +147,8 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
   }
   // 2+3 fused (one streaming pass) when the shape has an instantiation
   if (heff23_fused(h, dtype, d, clp, W1, W2, t0, t1, h->what, st)) {
-    int64_t ea[] = {cr, clp, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
-    int64_t eb[] = {cr, cr, wr};          int32_t mb[] = {mR, mRp, mC};
-    int64_t ec[] = {clp, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
     TNB_TRY(check_cuda(h, cudaGetLastError(), "heff23"));
-    return contract_impl(h, dtype, 5, ea, ma, t1, 3, eb, mb, R, 4, ec, mc, out, nullptr, nullptr, 0, st);
+    return step4(t1);
   }
   {  // 2. T2[s2,r,l',s1',b] = T1 W1[a,s1,s1',b]
     int64_t ea[] = {d1, d2, cr, clp, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
@@ -148,13 +162,8 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
     int64_t ec[] = {cr, clp, d1, d2, wr}; int32_t mc[] = {mR, mLp, mS1p, mS2p, mC};
     TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 4, eb, mb, W2, 5, ec, mc, t0, nullptr, nullptr, 0, st));
   }
-  {  // 4. out[l',s1',s2',r'] = T3 R[r,r',c]
-    int64_t ea[] = {cr, clp, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
-    int64_t eb[] = {cr, cr, wr};          int32_t mb[] = {mR, mRp, mC};
-    int64_t ec[] = {clp, d1, d2, cr};     int32_t mc[] = {mLp, mS1p, mS2p, mRp};
-    TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 3, eb, mb, R, 4, ec, mc, out, nullptr, nullptr, 0, st));
-  }
-  return TNB_OK;
+  // 4. out[l',s1',s2',r'] = T3 R[r,r',c]
+  return step4(t0);
 }
 
 static int check_dims(Handle* h, const tnb_bond_dims* d) {
@@ -192,6 +201,54 @@ int heff_apply_shard_impl(Handle* h, int dtype, const tnb_bond_dims* d, int64_t 
   TNB_TRY(ws_alloc(h, half, &t0));
   TNB_TRY(ws_alloc(h, half, &t1));
   return heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, out, t0, t1, st);
+}
+
+// Device-side barrier over peer-mapped flag arrays: lane g publishes `epoch` into rank g's flags[rank] (system-scope
+// release) and then waits until its own flags[g] has reached `epoch` (acquire).  Runs after the GEMM in stream order,
+// so every peer store of this rank is performed before its flag.  A bounded spin (about 10 s) protects against a
+// rank that never arrives: the kernel then records a failure in err[0] instead of hanging the GPU.
+__global__ void peer_barrier_kernel(unsigned long long* const* flags, int rank, int world, unsigned long long epoch,
+                                    double* err) {
+  const int g = threadIdx.x;
+  if (g >= world) return;
+  __threadfence_system();
+  unsigned long long* remote = flags[g] + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+  const unsigned long long* mine = flags[rank] + g;
+  const long long t0 = clock64();
+  unsigned long long v = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 20000000000LL) { err[0] = 1.0; break; }
+    __nanosleep(200);
+  }
+}
+
+int heff_apply_shard_fused_impl(Handle* h, int dtype, const tnb_bond_dims* d, int rank, int world, int64_t clp,
+                                const void* Lslab, const void* W1, const void* W2, const void* R, const void* phi,
+                                void* const* out_peers, void* const* flag_peers, unsigned long long epoch, cudaStream_t st) {
+  TNB_TRY(check_dims(h, d));
+  if (world < 1 || world > TNB_MAX_PEERS || rank < 0 || rank >= world) return set_err(h, TNB_ERR_BAD_ARG, "heff_apply_shard_fused: rank/world");
+  if (clp < 1 || clp * world != d->chiL) return set_err(h, TNB_ERR_BAD_ARG, "heff_apply_shard_fused: chiL must be world * lp_extent");
+  ws_reset(h);
+  const size_t base = (size_t)clp * d->chiR * d->d1 * d->d2;
+  const size_t w = std::max({d->wL, d->wM, d->wR});
+  const size_t half = al256(base * w * elsize(dtype));
+  TNB_TRY(ws_require(h, 2 * half + 4096));
+  void *t0, *t1, *fp;
+  TNB_TRY(ws_alloc(h, half, &t0));
+  TNB_TRY(ws_alloc(h, half, &t1));
+  TNB_TRY(ws_alloc(h, TNB_MAX_PEERS * sizeof(void*), &fp));
+  PeerOut po;
+  po.npeer = world;
+  // base[0] must be this rank's own buffer only for bookkeeping; order is irrelevant to the stores
+  for (int g = 0; g < world; ++g) po.base[g] = (char*)out_peers[g] + (size_t)rank * clp * elsize(dtype);
+  TNB_TRY(heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, nullptr, t0, t1, st, &po));
+  TNB_CUDA(h, cudaMemcpyAsync(fp, flag_peers, world * sizeof(void*), cudaMemcpyHostToDevice, st));
+  peer_barrier_kernel<<<1, 32, 0, st>>>((unsigned long long* const*)fp, rank, world, epoch, h->scal + 200);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "peer barrier");
 }
 
 // ------------------------------------------------------------------------------------
@@ -507,6 +564,62 @@ int tnb_heff_apply_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, i
   if (!h) return TNB_ERR_BAD_ARG;
   if (!L_slab || !W1 || !W2 || !R || !phi || !out_slab) return set_err(H, TNB_ERR_BAD_ARG, "heff_apply_shard: null pointer");
   return heff_apply_shard_impl(H, dtype, dims, lp_extent, L_slab, W1, W2, R, phi, out_slab, ST);
+}
+
+int tnb_heff_apply_shard_fused(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int rank, int world,
+                               int64_t lp_extent, const void* L_slab, const void* W1, const void* W2, const void* R,
+                               const void* phi, void* const* out_peers, void* const* flag_peers, uint64_t epoch,
+                               void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!L_slab || !W1 || !W2 || !R || !phi || !out_peers || !flag_peers)
+    return set_err(H, TNB_ERR_BAD_ARG, "heff_apply_shard_fused: null pointer");
+  for (int g = 0; g < world && g < TNB_MAX_PEERS; ++g)
+    if (!out_peers[g] || !flag_peers[g]) return set_err(H, TNB_ERR_BAD_ARG, "heff_apply_shard_fused: null peer pointer %d", g);
+  return heff_apply_shard_fused_impl(H, dtype, dims, rank, world, lp_extent, L_slab, W1, W2, R, phi, out_peers, flag_peers,
+                                     (unsigned long long)epoch, ST);
+}
+
+// ---- peer-mapped buffers (CUDA IPC): one process per GPU on one NVSwitch node
+int tnb_peer_alloc(tnb_handle_t h, size_t bytes, void** ptr, unsigned char* ipc_handle_out) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!ptr || !ipc_handle_out || bytes == 0) return set_err(H, TNB_ERR_BAD_ARG, "peer_alloc: bad argument");
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return set_err(H, TNB_ERR_ALLOC, "peer_alloc: cudaMalloc(%zu) failed", bytes); }
+  cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return check_cuda(H, e, "cudaIpcGetMemHandle"); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(ipc_handle_out, &hd, 64);
+  *ptr = p;
+  return TNB_OK;
+}
+
+int tnb_peer_open(tnb_handle_t h, const unsigned char* ipc_handle, void** ptr) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!ipc_handle || !ptr) return set_err(H, TNB_ERR_BAD_ARG, "peer_open: null pointer");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, 64);
+  return check_cuda(H, cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int tnb_peer_close(tnb_handle_t h, void* ptr) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  return check_cuda(H, cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle");
+}
+
+int tnb_peer_free(tnb_handle_t h, void* ptr) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  return check_cuda(H, cudaFree(ptr), "cudaFree(peer buffer)");
+}
+
+// 0 = every device-side peer barrier so far completed; TNB_ERR_NO_CONVERGENCE = one timed out.  Synchronises.
+int tnb_peer_status(tnb_handle_t h, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  TNB_CUDA(H, cudaMemcpyAsync(H->scal_host + 101, H->scal + 200, sizeof(double), cudaMemcpyDeviceToHost, ST));
+  TNB_CUDA(H, cudaStreamSynchronize(ST));
+  if (H->scal_host[101] != 0.0) return set_err(H, TNB_ERR_NO_CONVERGENCE, "peer barrier timed out (a rank never arrived)");
+  return TNB_OK;
 }
 
 int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,

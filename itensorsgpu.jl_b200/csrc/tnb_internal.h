@@ -11,6 +11,7 @@
 namespace tnb {
 
 constexpr int MAXG = 12;  // modes per group (M / N / K) after merging
+constexpr int TNB_MAX_PEERS = 8;   // GPUs of one NVSwitch node
 
 // One mode group of a contraction, linearised in mixed radix (ext[0] fastest).
 // sX / sY are the element strides of each mode in the two tensors that carry the group:
@@ -40,6 +41,9 @@ struct GemmParams {
   // split output: columns n >= splitN of batch b go to C + boffC2[b] (column index n - splitN)
   int splitN;
   const long long* boffC2;
+  // fused all-gather: when npeer > 0 the epilogue stores to every peerC[g] (same element offsets) instead of C
+  int npeer;
+  void* peerC[TNB_MAX_PEERS];
 };
 
 struct Handle {
@@ -85,6 +89,11 @@ int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32
                   const void* A, int nB, const int64_t* extB, const int32_t* modeB,
                   const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
                   const void* alpha, const void* beta, int flags, cudaStream_t st);
+int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
+                     const void* A, int nB, const int64_t* extB, const int32_t* modeB,
+                     const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                     const void* alpha, const void* beta, int flags, cudaStream_t st,
+                     const int64_t* strideC, void* const* peerC, int npeer);
 // plain column-major GEMM helper built on the same kernel:
 //   C[m x n] (ldc) <- alpha * op(A) * op(B) + beta * C ; op = N / T / C(onj-transpose)
 int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,

@@ -43,3 +43,106 @@ def heff_apply_sharded(ops, L_slab, W1, W2, R, phi, group=None):
     dist.all_gather_into_tensor(gathered, slab.data, group=group)
     cl, d1, d2, cr = phi.dims
     return assemble_gathered(gathered, cl, d1, d2, cr, world)
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused GEMM + all-gather over NVLink peer memory (tnb_heff_apply_shard_fused)
+# ---------------------------------------------------------------------------------------------
+class _RawCuda:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerBuffers:
+    """One buffer of ``nbytes`` per rank, each mapped into every process of the group (CUDA IPC): ``ptrs[g]`` is
+    rank g's buffer as seen from this process.  The 64-byte IPC handles travel through the host-side process
+    group; after that no library collective touches the data path."""
+
+    def __init__(self, nbytes, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        self.h = _lib.handle()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nbytes = int(nbytes)
+        own = C.c_void_p()
+        hbuf = C.create_string_buffer(64)
+        self.h.check(self.h.lib.tnb_peer_alloc(self.h.h, self.nbytes, C.byref(own), hbuf))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(hbuf.raw), group=group)
+        self.ptrs = []
+        for g, hb in enumerate(handles):
+            if g == self.rank:
+                self.ptrs.append(own.value)
+            else:
+                p = C.c_void_p()
+                self.h.check(self.h.lib.tnb_peer_open(self.h.h, hb, C.byref(p)))
+                self.ptrs.append(p.value)
+        self._arr = (C.c_void_p * self.world)(*self.ptrs)
+        dist.barrier(group=group)
+
+    def c_array(self):
+        return self._arr
+
+    def local(self, dtype=torch.float64):
+        """torch view of this rank's own buffer."""
+        return torch.as_tensor(_RawCuda(self.ptrs[self.rank], self.nbytes), device="cuda").view(dtype)
+
+    def close(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for g, p in enumerate(self.ptrs):
+            if g != self.rank:
+                self.h.lib.tnb_peer_close(self.h.h, p)
+        dist.barrier(group=self.group)
+        self.h.lib.tnb_peer_free(self.h.h, self.ptrs[self.rank])
+        self.ptrs = []
+
+
+class FusedShardedHeff:
+    """H_eff*phi with the output bond sharded over the ranks and the all-gather fused into the last GEMM:
+    every rank ends up with the FULL H*phi in its own ``out`` buffer (same layout as phi), written tile by tile by
+    all ranks through NVLink peer stores; a device-side flag barrier replaces the collective."""
+
+    def __init__(self, phi_dims, dtype=torch.float64, group=None, nbuf=2):
+        n = 1
+        for d in phi_dims:
+            n *= int(d)
+        es = 16 if dtype == torch.complex128 else 8
+        self.dims, self.dtype = tuple(phi_dims), dtype
+        self.outs = [PeerBuffers(n * es, group) for _ in range(nbuf)]
+        self.flags = PeerBuffers(8 * 8, group)
+        self.epoch = 0
+        self.rank, self.world = self.flags.rank, self.flags.world
+
+    def apply(self, Lslab, W1, W2, R, phi):
+        """Returns a DTensor view of this rank's full-vector buffer holding H*phi (valid for work queued behind the
+        call on the current stream; buffers alternate between calls)."""
+        import ctypes as C
+        from . import ops
+        from .ops import DTensor, BondDims
+        h = self.flags.h
+        cl, d1, d2, cr = phi.dims
+        clp = Lslab.dims[1]
+        bd = BondDims(cl, cr, d1, d2, W1.dims[0], W1.dims[3], W2.dims[3])
+        buf = self.outs[self.epoch % len(self.outs)]
+        self.epoch += 1
+        h.check(h.lib.tnb_heff_apply_shard_fused(h.h, ops._dt(phi.data), C.byref(bd), self.rank, self.world, clp,
+                                                 ops._ptr(Lslab.data), ops._ptr(W1.data), ops._ptr(W2.data), ops._ptr(R.data),
+                                                 ops._ptr(phi.data), buf.c_array(), self.flags.c_array(),
+                                                 C.c_uint64(self.epoch), ops._stream()))
+        return DTensor(buf.local(self.dtype), self.dims)
+
+    def status(self):
+        h = self.flags.h
+        from . import ops
+        h.check(h.lib.tnb_peer_status(h.h, ops._stream()))
+
+    def close(self):
+        for b in self.outs:
+            b.close()
+        self.flags.close()

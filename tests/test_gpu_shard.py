@@ -31,3 +31,60 @@ def test_heff_apply_shard_slabs(world, cplx):
         slabs.append(out.data)
     full = tn.shard.assemble_gathered(torch.cat(slabs), chi, d, d, cr, world)
     assert ot.rel_err(full.cpu().numpy().reshape((chi, d, d, cr), order="F"), want) < 1e-12
+
+
+def _fused_worker(rank, world, port, q, cplx):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from itensorsgpu_b200 import tn
+    rng = np.random.default_rng(52)
+    chi, cr, d, w = 64, 48, 2, 5
+    L = rand(rng, (chi, chi, w), cplx); R = rand(rng, (cr, cr, w), cplx)
+    W1 = rand(rng, (w, d, d, w), cplx); W2 = rand(rng, (w, d, d, w), cplx)
+    phis = [rand(rng, (chi, d, d, cr), cplx) for _ in range(3)]
+    D = tn.DTensor.from_numpy
+    dL = D(L)
+    lo, hi = tn.shard.slab_range(chi, rank, world)
+    Ls = tn.DTensor(tn.shard.left_env_slab(dL.data, chi, w, rank, world), (chi, hi - lo, w))
+    fh = tn.shard.FusedShardedHeff((chi, d, d, cr), torch.complex128 if cplx else torch.float64)
+    errs = []
+    for phi in phis:                                   # three epochs, alternating buffers
+        out = fh.apply(Ls, D(W1), D(W2), D(R), D(phi))
+        torch.cuda.synchronize()
+        errs.append(ot.rel_err(out.numpy(), od.heff_apply(L, W1, W2, R, phi)))
+    fh.status()
+    dist.barrier()
+    fh.close()
+    q.put((rank, max(errs)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_heff_shard_fused_gather_two_gpus(cplx):
+    """GEMM + all-gather fused over NVLink peer memory (tnb_heff_apply_shard_fused): every rank must hold the full
+    H*phi after the call, with no NCCL data collective."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 2000) + int(cplx)
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, q, cplx)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(e < 1e-12 for _, e in res)
