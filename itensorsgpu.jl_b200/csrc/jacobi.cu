@@ -27,6 +27,10 @@ namespace tnb {
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+size_t eigh_dc_ws_bytes(int dtype, int64_t n, int64_t kmax);
+int eigh_dc_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu,
+                 cudaStream_t st);
+
 template <bool CPLX> struct JT { using T = double; static constexpr int NB2 = 64; };
 template <> struct JT<true> { using T = double2; static constexpr int NB2 = 64; };
 constexpr int EIG_THREADS = 512;
@@ -288,6 +292,39 @@ __global__ void symmetrize_upper_kernel(typename JT<CPLX>::T* A, long long n) {
 // ------------------------------------------------------------------------------------
 // driver
 // ------------------------------------------------------------------------------------
+// Convergence test of the whole column set at once: largest normalised off-diagonal entry of the n x n Gram
+// matrix (same null-column rule as small_eigh_kernel).  One DMMA GEMM + this kernel cost ~1/40 of a Jacobi
+// sweep, so the driver never spends a full sweep just to find out that the previous one had converged.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gram_offmax_kernel(const typename JT<CPLX>::T* __restrict__ G, long long n,
+                                                          const double* __restrict__ anorm, double* out) {
+  using T = typename JT<CPLX>::T;
+  const double delta2 = 3.2e-30 * anorm[0] * anorm[0];
+  double mx = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e % n, j = e / n;
+    if (i >= j) continue;
+    const T gii = G[i + i * n], gjj = G[j + j * n], gij = G[e];
+    double di, dj, a;
+    if constexpr (CPLX) { di = gii.x; dj = gjj.x; a = gij.x * gij.x + gij.y * gij.y; }
+    else { di = gii; dj = gjj; a = gij * gij; }
+    if (a > 0.0 && !(di < delta2 && dj < delta2)) {
+      const double d = fmax(di, delta2) * fmax(dj, delta2);
+      mx = fmax(mx, d > 0.0 ? a / d : 1e300);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m2 = 0;
+    for (int i = 0; i < 8; ++i) m2 = fmax(m2, red[i]);
+    atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(fmin(sqrt(m2), 1e300)));
+  }
+}
+
 struct JacobiOut {
   void* G;        // converged columns (orthogonal), m rows, leading dimension ldg
   void* V;        // accumulated rotations (A V = G), n rows, leading dimension ldv
@@ -310,7 +347,7 @@ size_t jacobi_ws_bytes(int dtype, int64_t m, int64_t n, bool want_v) {
   jacobi_geometry(dtype, n, &nblk, &npad);
   const size_t es = elsize(dtype);
   const int64_t mz = m + (want_v ? n : 0);
-  size_t tot = 2 * al256((size_t)mz * npad * es);
+  size_t tot = 2 * al256((size_t)mz * npad * es) + al256((size_t)npad * npad * es);
   tot += 2 * al256((size_t)(nblk / 2) * NB2 * NB2 * es);   // S and W batches
   tot += 2 * al256((size_t)nblk * sizeof(long long));      // offset tables
   tot += 2 * al256(64);
@@ -321,7 +358,7 @@ size_t jacobi_ws_bytes(int dtype, int64_t m, int64_t n, bool want_v) {
 // A (m x n, column-major, lda) is copied in; result buffers live in the arena.
 template <bool CPLX>
 static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda, bool want_v, JacobiOut* out,
-                      int* sweeps_done, cudaStream_t st) {
+                      int* sweeps_done, cudaStream_t st, const void* V0 = nullptr, int64_t ldv0 = 0) {
   using T = typename JT<CPLX>::T;
   constexpr int NB2 = JT<CPLX>::NB2;
   constexpr int b = NB2 / 2;
@@ -331,7 +368,8 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   const int k = (int)(nblk / 2);
   const size_t es = sizeof(T);
   const int64_t mz = m + (want_v ? n : 0);
-  void *Z0, *Z1, *Sb, *Wb, *tC1, *tC2, *dscal, *danorm;
+  void *Z0, *Z1, *Sb, *Wb, *tC1, *tC2, *dscal, *danorm, *Gbig;
+  TNB_TRY(ws_alloc(h, (size_t)npad * npad * es, &Gbig));
   TNB_TRY(ws_alloc(h, (size_t)mz * npad * es, &Z0));
   TNB_TRY(ws_alloc(h, (size_t)mz * npad * es, &Z1));
   TNB_TRY(ws_alloc(h, (size_t)k * NB2 * NB2 * es, &Sb));
@@ -346,6 +384,8 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   if (want_v) {
     set_identity_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)Z0 + m, mz, n, npad);
     h->launches++;
+    if (V0)   // preconditioned start: A is already A_orig * V0
+      TNB_CUDA(h, cudaMemcpy2DAsync((T*)Z0 + m, (size_t)mz * es, V0, (size_t)ldv0 * es, (size_t)n * es, (size_t)n, cudaMemcpyDeviceToDevice, st));
   }
   // ||A||_F for the null-column threshold (contiguous input only; otherwise norm of the padded copy's top rows
   // is the same number, computed column-block-wise by nrm2 over Z0 would include the identity -> use A)
@@ -380,7 +420,21 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   void* Zs[2] = {Z0, Z1};
   int sweep = 0;
   const int max_sweeps = 40;
-  for (; sweep < max_sweeps; ++sweep) {
+  // whole-matrix convergence test (one GEMM + one reduction): true when every pair is orthogonal to tol
+  auto converged = [&](bool* yes) -> int {
+    TNB_TRY(gemm_impl(h, dtype, 'C', 'N', npad, npad, m, nullptr, Zs[cur], mz, Zs[cur], mz, nullptr, Gbig, npad, st));
+    TNB_CUDA(h, cudaMemsetAsync(dscal, 0, 8, st));
+    gram_offmax_kernel<CPLX><<<h->num_sms * 4, 256, 0, st>>>((const T*)Gbig, npad, (const double*)danorm, (double*)dscal);
+    h->launches++;
+    TNB_CUDA(h, cudaMemcpyAsync(h->scal_host + 100, dscal, 8, cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(h, cudaStreamSynchronize(st));
+    *yes = h->scal_host[100] < tol;
+    return TNB_OK;
+  };
+  const bool use_check = (lda == m);      // needs ||A||_F for the null-column rule
+  bool done = false;
+  if (use_check && V0) TNB_TRY(converged(&done));
+  for (; !done && sweep < max_sweeps; ++sweep) {
     TNB_CUDA(h, cudaMemsetAsync(dscal, 0, 8, st));
     for (int s = 0; s < steps; ++s) {
       // 1. Gram of every pair (top m rows of Z only)
@@ -399,7 +453,11 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
     TNB_CUDA(h, cudaGetLastError());
     TNB_CUDA(h, cudaMemcpyAsync(h->scal_host + 100, dscal, 8, cudaMemcpyDeviceToHost, st));
     TNB_CUDA(h, cudaStreamSynchronize(st));
-    if (h->scal_host[100] < tol) { ++sweep; break; }
+    if (h->scal_host[100] < tol) { ++sweep; break; }      // nothing above tol was seen during this sweep
+    if (use_check && npad >= 256) {                        // did this sweep finish the job?
+      TNB_TRY(converged(&done));
+      if (done) { ++sweep; break; }
+    }
   }
   if (sweeps_done) *sweeps_done = sweep;
   if (sweep >= max_sweeps && !(h->scal_host[100] < tol * 100))
@@ -449,7 +507,26 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
   }
   JacobiOut jo;
   int sweeps = 0;
-  TNB_TRY(jacobi_run<CPLX>(h, mm, nn, Awork, ld, true, &jo, &sweeps, st));
+  // Preconditioning (n >= SVD_PRECOND_MIN): V0 from the Hermitian eigensolver on A^H A, B = A V0 has columns that
+  // are already orthogonal up to eps*kappa^2 and sorted by norm, so the Jacobi iteration (which restores full
+  // LAPACK-class accuracy for the small singular values) needs 1-2 sweeps instead of 8-10.
+  const char* pe = getenv("TNB_SVD_PRECOND_MIN");
+  const int64_t pmin = pe ? atoll(pe) : 256;
+  if (pmin > 0 && nn >= pmin && ld == mm) {
+    void *rho, *V0, *Bm, *Dv;
+    TNB_TRY(ws_alloc(h, (size_t)nn * nn * sizeof(T), &rho));
+    TNB_TRY(ws_alloc(h, (size_t)nn * nn * sizeof(T), &V0));
+    TNB_TRY(ws_alloc(h, (size_t)mm * nn * sizeof(T), &Bm));
+    TNB_TRY(ws_alloc(h, (size_t)nn * sizeof(double), &Dv));
+    TNB_TRY(gemm_impl(h, dtype, 'C', 'N', nn, nn, mm, nullptr, Awork, ld, Awork, ld, nullptr, rho, nn, st));
+    const size_t mark = h->ws_off;
+    TNB_TRY(eigh_dc_impl(h, dtype, nn, rho, nn, nn, (double*)Dv, V0, nn, st));
+    h->ws_off = mark;
+    TNB_TRY(gemm_impl(h, dtype, 'N', 'N', mm, nn, nn, nullptr, Awork, ld, V0, nn, nullptr, Bm, mm, st));
+    TNB_TRY(jacobi_run<CPLX>(h, mm, nn, Bm, mm, true, &jo, &sweeps, st, V0, nn));
+  } else {
+    TNB_TRY(jacobi_run<CPLX>(h, mm, nn, Awork, ld, true, &jo, &sweeps, st));
+  }
   void *nrm, *perm, *sorted;
   TNB_TRY(ws_alloc(h, jo.npad * sizeof(double), &nrm));
   TNB_TRY(ws_alloc(h, jo.npad * sizeof(int), &perm));
@@ -481,7 +558,9 @@ size_t svd_ws_bytes(int dtype, int64_t m, int64_t n) {
   const int64_t mm = std::max(m, n), nn = std::min(m, n);
   int64_t nblk, npad;
   jacobi_geometry(dtype, nn, &nblk, &npad);
-  return jacobi_ws_bytes(dtype, mm, nn, true) + al256((size_t)m * n * elsize(dtype)) + 3 * al256(npad * 8) + 4096;
+  const size_t es = elsize(dtype);
+  const size_t pre = 2 * al256((size_t)nn * nn * es) + al256((size_t)mm * nn * es) + al256(nn * 8) + eigh_dc_ws_bytes(dtype, nn, nn);
+  return jacobi_ws_bytes(dtype, mm, nn, true) + al256((size_t)m * n * es) + 3 * al256(npad * 8) + pre + 4096;
 }
 
 int svd_impl(Handle* h, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, int64_t kmax, int64_t ks, void* U,
@@ -546,9 +625,6 @@ static int eigh_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks, do
 // rank-deficient density matrix stall at relative off-diagonals ~eps*lambda_max/lambda_j.)  Jacobi stays selectable,
 // via TNB_EIGH=jacobi (A/B measurements); TNB_EIGH=dc forces the new path for every n >= 2 as well.
 constexpr int64_t EIGH_DC_MIN = 2;
-size_t eigh_dc_ws_bytes(int dtype, int64_t n, int64_t kmax);
-int eigh_dc_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks, double* D, void* U, int64_t ldu,
-                 cudaStream_t st);
 static bool eigh_use_dc(int64_t n) {
   const char* e = getenv("TNB_EIGH");     // read per call: tests flip it inside one process
   const int mode = (e && !strcmp(e, "jacobi")) ? 1 : (e && !strcmp(e, "dc")) ? 2 : 0;
