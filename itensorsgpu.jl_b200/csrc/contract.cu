@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
     tn = w / gsz;
   }
   const int m0 = tm * BM, n0 = tn * BN;
+  if (p.lowerOnly && m0 + BM <= n0) return;      // tile strictly above the diagonal of a Hermitian update
 
   using LA = Loader<CPLX, AK, VA, BM, BK, NT, false>;
   using LB = Loader<CPLX, BKM, VB, BN, BK, NT, true>;
@@ -370,6 +371,57 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
     offm[i] = okm[i] ? decode<true>(p.gm, m) : 0;
   }
   const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
+  if (has_beta && p.npeer == 0) {
+    // beta != 0: read-modify-write.  Loads of C cannot be hoisted over stores to C by the compiler, and one
+    // dependent global round trip per element (64 per thread) made a K=128 update epilogue-bound (9 TFLOP/s):
+    // fetch the 2*MI old values of a column slice first, then combine and store.
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      long long offn[2];
+      bool okn[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = n0 + wn0 + j * 8 + lc * 2 + e;
+        okn[e] = n < p.N;
+        offn[e] = 0;
+        if (okn[e]) {
+          if (p.splitN && n >= p.splitN) offn[e] = decode<true>(p.gn, n - p.splitN) + (p.boffC2[blockIdx.y] - p.boffC[blockIdx.y]);
+          else offn[e] = decode<true>(p.gn, n);
+        }
+      }
+      if (!CPLX) {
+        double old[2][MI];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int i = 0; i < MI; ++i) old[e][i] = (okn[e] && okm[i]) ? ((const double*)Cb)[offm[i] + offn[e]] : 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+            if (okn[e] && okm[i]) ((double*)Cb)[offm[i] + offn[e]] = p.alpha_re * acc[i][j][e] + p.beta_re * old[e][i];
+      } else {
+        double2 old[2][MI];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int i = 0; i < MI; ++i) old[e][i] = (okn[e] && okm[i]) ? ((const double2*)Cb)[offm[i] + offn[e]] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+            if (okn[e] && okm[i]) {
+              const double xr = acc[i][j][e], xi = acc[i][j][2 + e];
+              const double2 o = old[e][i];
+              double2 v;
+              v.x = p.alpha_re * xr - p.alpha_im * xi + p.beta_re * o.x - p.beta_im * o.y;
+              v.y = p.alpha_re * xi + p.alpha_im * xr + p.beta_re * o.y + p.beta_im * o.x;
+              ((double2*)Cb)[offm[i] + offn[e]] = v;
+            }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < NI; ++j) {
 #pragma unroll
@@ -383,13 +435,11 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
       for (int i = 0; i < MI; ++i) {
         if (!okm[i]) continue;
         if (!CPLX) {
-          double v = p.alpha_re * acc[i][j][e];
+          const double v = p.alpha_re * acc[i][j][e];
           if (p.npeer > 0) {      // fused all-gather: same element to every GPU's buffer (NVLink peer stores)
             for (int g = 0; g < p.npeer; ++g) ((double*)p.peerC[g])[offm[i] + offn] = v;
           } else {
-            double* c = (double*)Cb + offm[i] + offn;
-            if (has_beta) v += p.beta_re * (*c);
-            *c = v;
+            ((double*)Cb)[offm[i] + offn] = v;
           }
         } else {
           const double xr = acc[i][j][e], xi = acc[i][j][2 + e];
@@ -399,13 +449,7 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
           if (p.npeer > 0) {
             for (int g = 0; g < p.npeer; ++g) ((double2*)p.peerC[g])[offm[i] + offn] = v;
           } else {
-            double2* c = (double2*)Cb + offm[i] + offn;
-            if (has_beta) {
-              const double2 o = *c;
-              v.x += p.beta_re * o.x - p.beta_im * o.y;
-              v.y += p.beta_re * o.y + p.beta_im * o.x;
-            }
-            *c = v;
+            ((double2*)Cb)[offm[i] + offn] = v;
           }
         }
       }
@@ -674,10 +718,11 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
 
 int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
               const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
-              const void* beta, void* C, int64_t ldc, cudaStream_t st) {
+              const void* beta, void* C, int64_t ldc, cudaStream_t st, int lower_only) {
   if (m == 0 || n == 0) return TNB_OK;
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.lowerOnly = lower_only;
   p.gm.n = p.gn.n = p.gk.n = 1;
   p.gm.ext[0] = (int)m; p.gn.ext[0] = (int)n; p.gk.ext[0] = (int)std::max<int64_t>(k, 1);
   // op: 'N' none, 'T' transpose, 'C' conjugate transpose, 'J' conjugate (no transpose)

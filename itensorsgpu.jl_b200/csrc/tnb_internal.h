@@ -41,6 +41,9 @@ struct GemmParams {
   // split output: columns n >= splitN of batch b go to C + boffC2[b] (column index n - splitN)
   int splitN;
   const long long* boffC2;
+  // lowerOnly: C is Hermitian and only its lower triangle (m >= n) is needed: CTAs whose tile lies strictly above
+  // the diagonal exit at once (syr2k-style trailing update of the tridiagonalisation)
+  int lowerOnly;
   // fused all-gather: when npeer > 0 the epilogue stores to every peerC[g] (same element offsets) instead of C
   int npeer;
   void* peerC[TNB_MAX_PEERS];
@@ -98,7 +101,7 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
 //   C[m x n] (ldc) <- alpha * op(A) * op(B) + beta * C ; op = N / T / C(onj-transpose)
 int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,
               const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
-              const void* beta, void* C, int64_t ldc, cudaStream_t st);
+              const void* beta, void* C, int64_t ldc, cudaStream_t st, int lower_only = 0);
 
 // batched column-major GEMM: for b in [0,batch): C_b = alpha*op(A_b)*op(B_b) + beta*C_b where
 // X_b = X + (offX ? offX[b] : b*strideX) elements.  offX are DEVICE arrays.

@@ -37,13 +37,15 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
                                                      typename ElemT<CPLX>::T* ZR, long long ldz,
                                                      const typename ElemT<CPLX>::T* __restrict__ ybuf,
                                                      const typename ElemT<CPLX>::T* __restrict__ yparts, int nparts,
+                                                     const typename ElemT<CPLX>::T* __restrict__ P, int nbt,
                                                      typename ElemT<CPLX>::T* tau, double* d, double* e,
                                                      typename ElemT<CPLX>::T* scal, double* partials, unsigned* counter) {
   using T = typename ElemT<CPLX>::T;
   constexpr int nb = TD_NB;
   __shared__ T p_s[nb], q_s[nb], rowW[nb], rowV[nb];
   __shared__ T redT[8];
-  __shared__ T accS[8][32], colS[8][32];
+  __shared__ T accS[8][32], colS[8][32], yS[8][32];
+  constexpr int TS = 128;     // = TD_TS: slot length of the symmetric matvec's partial buffer
   __shared__ double redD[8];
   __shared__ T bc[2];
   __shared__ int is_last;
@@ -65,7 +67,20 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
   const bool fin = (warp == 0 && active);
   const T a_in = (fin && do_column) ? A[r + (size_t)i * n] : a_zero<T>();
   const T vp = (fin && jp >= 0) ? vprev[r] : a_zero<T>();
-  const T yr = (fin && jp >= 0) ? ybuf[r - i] : a_zero<T>();
+  // y of the previous column: either final values (K2) or the per-tile slots of the symmetric matvec (K2S),
+  // which are summed here in a fixed order (warp w takes slots w, w+8, ...)
+  T yr = (fin && jp >= 0 && nbt == 0) ? ybuf[r - i] : a_zero<T>();
+  T ysl = a_zero<T>(), y0 = a_zero<T>();
+  if (jp >= 0 && nbt > 0) {
+    if (active) {
+      const long long t = r - i;
+      const T* src = P + ((size_t)(t / TS) * nbt) * TS + (t % TS);
+      for (int k = warp; k < nbt; k += 8) ysl = a_add(ysl, src[(size_t)k * TS]);
+    }
+    if (warp == 0) {                      // y at the pivot row (t = 0), needed by lane 0 below
+      for (int k = lane; k < nbt; k += 32) y0 = a_add(y0, P[(size_t)k * TS]);
+    }
+  }
   T zi_v = a_zero<T>(), zi_w = a_zero<T>(), zi_v2 = a_zero<T>(), zi_w2 = a_zero<T>();   // row i of the panel (warp 0)
   if (warp == 0 && jp > 0) {
     if (lane < jp) { zi_v = ZL[i + (size_t)lane * ldz]; zi_w = ZL[i + (size_t)(nb + lane) * ldz]; }
@@ -97,6 +112,7 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) pq += __shfl_xor_sync(0xffffffffu, pq, o);
       wacc = a_warp_sum(wacc);
+      if (nbt > 0) y0 = a_warp_sum(y0);
       if (lane == 0) {
         T yhv = a_zero<T>();
         for (int w = 0; w < 8; ++w) yhv = a_add(yhv, redT[w]);
@@ -104,7 +120,8 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
         const T al2 = a_scale(a_mul(tau_p, wphv), -0.5);
         bc[0] = al2;
         const T vpi = vprev[i];
-        const T wi = a_add(a_mul(tau_p, a_sub(ybuf[0], wacc)), a_mul(al2, vpi));
+        const T ypiv = (nbt > 0) ? y0 : ybuf[0];
+        const T wi = a_add(a_mul(tau_p, a_sub(ypiv, wacc)), a_mul(al2, vpi));
         rowW[jp] = a_conj(wi);
         rowV[jp] = a_conj(vpi);
       }
@@ -124,12 +141,17 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
   }
   accS[warp][lane] = acc;
   colS[warp][lane] = ca;
+  yS[warp][lane] = ysl;
   __syncthreads();
   double part2 = 0.0;
   if (fin) {
     T accsum = a_zero<T>(), casum = a_zero<T>();
 #pragma unroll
     for (int w = 0; w < 8; ++w) { accsum = a_add(accsum, accS[w][lane]); casum = a_add(casum, colS[w][lane]); }
+    if (nbt > 0) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) yr = a_add(yr, yS[w][lane]);
+    }
     T a = do_column ? a_sub(a_in, casum) : a_zero<T>();
     if (jp >= 0) {
       const T wr = a_add(a_mul(tau_p, a_sub(yr, accsum)), a_mul(alpha2, vp));
@@ -352,14 +374,17 @@ __device__ __forceinline__ double ld_stream(const double* p) {
 __device__ __forceinline__ double2 ld_stream(const double2* p) { return ld_stream16(p); }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(256) td_k2s_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i, int j,
+__global__ void __launch_bounds__(256, CPLX ? 2 : 3) td_k2s_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i, int j,
                                                       typename ElemT<CPLX>::T* ZL, typename ElemT<CPLX>::T* ZR, long long ldz,
                                                       const typename ElemT<CPLX>::T* __restrict__ scal,
                                                       typename ElemT<CPLX>::T* __restrict__ P, int nbt, int ntiles,
-                                                      typename ElemT<CPLX>::T* __restrict__ ybuf) {
+                                                      typename ElemT<CPLX>::T* __restrict__ ybuf,
+                                                      typename ElemT<CPLX>::T* __restrict__ yparts) {
   using T = typename ElemT<CPLX>::T;
   constexpr int nb = TD_NB, TS = TD_TS;
+  constexpr int CB = CPLX ? 2 : 4;      // columns per load batch: 4*CB independent loads in flight per lane
   __shared__ T vI[TS], vJ[TS], colres[TS];
+  __shared__ T yvred[4];
   __shared__ T rowacc[8][TS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long r0 = i + 1;
@@ -408,10 +433,10 @@ __global__ void __launch_bounds__(256) td_k2s_kernel(const typename ElemT<CPLX>:
   for (int q = 0; q < 4; ++q) { vr[q] = vI[lane + 32 * q]; yr[q] = a_zero<T>(); rok[q] = (I * TS + lane + 32 * q) < nt; }
   const T* base = A + (r0 + (size_t)I * TS + lane) + (size_t)(r0 + (size_t)J * TS) * n;
 #pragma unroll 1
-  for (int cb = 0; cb < TS / 8; cb += 8) {
-    T av[8][4];
+  for (int cb = 0; cb < TS / 8; cb += CB) {
+    T av[CB][4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < CB; ++u) {
       const int c = warp + 8 * (cb + u);
       const bool cok = (J * TS + c) < nt;
 #pragma unroll
@@ -422,7 +447,7 @@ __global__ void __launch_bounds__(256) td_k2s_kernel(const typename ElemT<CPLX>:
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < CB; ++u) {
       const int c = warp + 8 * (cb + u);
       const T vc = vJ[c];
       T s = a_zero<T>();
@@ -442,45 +467,31 @@ __global__ void __launch_bounds__(256) td_k2s_kernel(const typename ElemT<CPLX>:
     T rs = a_zero<T>();
 #pragma unroll
     for (int w = 0; w < 8; ++w) rs = a_add(rs, rowacc[w][tid]);
-    if (diag) P[((size_t)I * nbt + I) * TS + tid] = a_add(rs, colres[tid]);
-    else {
+    T yv;                                 // this tile's share of y^H v
+    if (diag) {
+      const T y = a_add(rs, colres[tid]);
+      P[((size_t)I * nbt + I) * TS + tid] = y;
+      yv = a_cmul(y, vI[tid]);
+    } else {
       P[((size_t)I * nbt + J) * TS + tid] = rs;
       P[((size_t)J * nbt + I) * TS + tid] = colres[tid];
+      yv = a_add(a_cmul(rs, vI[tid]), a_cmul(colres[tid], vJ[tid]));
     }
+    yv = a_warp_sum(yv);
+    if (lane == 0) yvred[warp] = yv;
   }
+  __syncthreads();
+  if (tid == 0) yparts[blockIdx.x] = a_add(a_add(yvred[0], yvred[1]), a_add(yvred[2], yvred[3]));
 }
 
-// y[t] = sum_k P[block(t)][k][t % TS]; also this CTA's share of y^H v
-template <bool CPLX>
-__global__ void __launch_bounds__(256) td_k2r_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i,
-                                                      const typename ElemT<CPLX>::T* __restrict__ scal,
-                                                      const typename ElemT<CPLX>::T* __restrict__ P, int nbt,
-                                                      typename ElemT<CPLX>::T* __restrict__ ybuf,
-                                                      typename ElemT<CPLX>::T* __restrict__ yparts) {
-  using T = typename ElemT<CPLX>::T;
-  constexpr int TS = TD_TS;
-  __shared__ T wsum[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long r0 = i + 1;
-  const int nt = (int)(n - r0);
-  const int t = blockIdx.x * 256 + tid;
-  T yv = a_zero<T>();
-  if (t < nt) {
-    const T* src = P + ((size_t)(t / TS) * nbt) * TS + (t % TS);
-    T y = a_zero<T>();
-#pragma unroll 8
-    for (int k = 0; k < nbt; ++k) y = a_add(y, src[(size_t)k * TS]);
-    ybuf[t] = y;
-    const T v = (t == 0) ? a_one<T>() : a_mul(A[r0 + t + (size_t)i * n], scal[0]);
-    yv = a_cmul(y, v);
-  }
-  yv = a_warp_sum(yv);
-  if (lane == 0) wsum[warp] = yv;
-  __syncthreads();
-  if (tid == 0) {
-    T s = a_zero<T>();
-    for (int w = 0; w < 8; ++w) s = a_add(s, wsum[w]);
-    yparts[blockIdx.x] = s;
+// lower triangle -> upper triangle (conjugated) of the trailing block A[lo:, lo:], used once when the
+// reduction switches from the lower-only (symmetric) kernels to the full-column ones
+template <typename T>
+__global__ void td_mirror_kernel(T* A, long long n, long long lo) {
+  const long long m = n - lo;
+  for (long long eidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; eidx < m * m; eidx += (long long)gridDim.x * blockDim.x) {
+    const long long r = eidx % m, c = eidx / m;
+    if (r > c) A[(lo + c) + (size_t)(lo + r) * n] = a_conj(A[(lo + r) + (size_t)(lo + c) * n]);
   }
 }
 
@@ -532,18 +543,21 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
   TNB_TRY(ws_alloc(h, (size_t)n * 2 * nb * sizeof(T), &ZRv));
   TNB_TRY(ws_alloc(h, (size_t)(n + 2 * nb) * sizeof(T), &yv));
   TNB_TRY(ws_alloc(h, 64, &scv));
-  TNB_TRY(ws_alloc(h, (size_t)std::max<int64_t>(h->num_sms * 4, n / 256 + 2) * sizeof(T), &ypv));
+  const size_t nbt_max = (size_t)(n + TD_TS - 1) / TD_TS;
+  TNB_TRY(ws_alloc(h, std::max<size_t>((size_t)h->num_sms * 4, nbt_max * (nbt_max + 1) / 2 + 8) * sizeof(T), &ypv));
   T *ZL = (T*)ZLv, *ZR = (T*)ZRv, *ybuf = (T*)yv, *scal = (T*)scv, *yparts = (T*)ypv;
   int nparts = 0;
   // symmetric (half-traffic) matvec for trailing sizes >= sym_min; TNB_TD_SYM_MIN overrides, 0 disables
   const char* sm_env = getenv("TNB_TD_SYM_MIN");
-  const int64_t sym_min = sm_env ? atoll(sm_env) : 3072;
+  const int64_t sym_min = sm_env ? atoll(sm_env) : 1536;
   void* Pv = nullptr;
   if (sym_min > 0 && n - 1 >= sym_min) {
     const size_t nbt = (size_t)(n + TD_TS - 1) / TD_TS;
     TNB_TRY(ws_alloc(h, nbt * nbt * TD_TS * sizeof(T), &Pv));
   }
   T* P = (T*)Pv;
+  int nbt_prev = 0;            // > 0: the previous column's y lives in P slots (K2S), else in ybuf (K2)
+  bool lower_valid_only = false;
   static bool attr_done = false;
   if (!attr_done) {
     TNB_CUDA(h, cudaFuncSetAttribute(td_k2_kernel<CPLX, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -554,7 +568,8 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
   const double one[2] = {1.0, 0.0}, mone[2] = {-1.0, 0.0};
   auto k1 = [&](int64_t i, int jp, int do_column) {
     const int grid = (int)((n - i + 31) / 32);
-    td_k1_kernel<CPLX><<<grid, 256, 0, st>>>(A, n, i, jp, do_column, ZL, ZR, n, ybuf, yparts, nparts, tau, d, e, scal, h->partials, h->counter);
+    td_k1_kernel<CPLX><<<grid, 256, 0, st>>>(A, n, i, jp, do_column, ZL, ZR, n, ybuf, yparts, nparts, P, nbt_prev, tau, d, e, scal,
+                                             h->partials, h->counter);
     h->launches++;
   };
   for (int64_t p0 = 0; p0 < n - 1; p0 += nb) {
@@ -563,26 +578,40 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
       TNB_CUDA(h, cudaMemsetAsync(ZL, 0, (size_t)n * 2 * nb * sizeof(T), st));
       TNB_CUDA(h, cudaMemsetAsync(ZR, 0, (size_t)n * 2 * nb * sizeof(T), st));
     }
+    // a panel takes the symmetric (lower-triangle-only) kernels iff every one of its columns is large enough
+    const bool panel_sym = P && (n - (p0 + jb)) >= sym_min;
+    if (!panel_sym && lower_valid_only) {      // switching to full-column kernels: rebuild the upper triangle once
+      td_mirror_kernel<T><<<h->num_sms * 4, 256, 0, st>>>(A, n, p0);
+      h->launches++;
+      lower_valid_only = false;
+    }
     for (int j = 0; j < jb; ++j) {
       const int64_t i = p0 + j;
       k1(i, j - 1, 1);
       const int Ct = (int)(n - i - 1) + 2 * j;
       const int nt = (int)(n - i - 1);
-      if (P && nt >= sym_min) {
+      if (panel_sym) {
         const int nbt = (nt + TD_TS - 1) / TD_TS;
         const int ntiles = nbt * (nbt + 1) / 2;
-        td_k2s_kernel<CPLX><<<ntiles + (2 * j + 7) / 8, 256, 0, st>>>(A, n, i, j, ZL, ZR, n, scal, P, nbt, ntiles, ybuf);
-        nparts = (nt + 255) / 256;
-        td_k2r_kernel<CPLX><<<nparts, 256, 0, st>>>(A, n, i, scal, P, nbt, ybuf, yparts);
-        h->launches += 2;
-      } else if (Ct >= 2 * 32 * h->num_sms) nparts = launch_k2<CPLX, 2>(h, A, n, i, j, ZL, ZR, n, scal, ybuf, yparts, st);
+        td_k2s_kernel<CPLX><<<ntiles + (2 * j + 7) / 8, 256, 0, st>>>(A, n, i, j, ZL, ZR, n, scal, P, nbt, ntiles, ybuf, yparts);
+        nparts = ntiles;
+        nbt_prev = nbt;
+        h->launches++;
+        continue;
+      }
+      nbt_prev = 0;
+      if (Ct >= 2 * 32 * h->num_sms) nparts = launch_k2<CPLX, 2>(h, A, n, i, j, ZL, ZR, n, scal, ybuf, yparts, st);
       else nparts = launch_k2<CPLX, 1>(h, A, n, i, j, ZL, ZR, n, scal, ybuf, yparts, st);
     }
     const int64_t lo = p0 + jb;
     k1(lo, jb - 1, 0);
     const int64_t ntr = n - lo;
-    TNB_TRY(gemm_impl(h, dtype, 'N', 'C', ntr, ntr, 2 * nb, mone, ZL + lo, n, ZR + lo, n, one, A + lo + (size_t)lo * n, n, st));
+    // after a symmetric panel only the lower triangle is kept up to date (syr2k-style: half the update)
+    TNB_TRY(gemm_impl(h, dtype, 'N', 'C', ntr, ntr, 2 * nb, mone, ZL + lo, n, ZR + lo, n, one, A + lo + (size_t)lo * n, n, st,
+                      panel_sym ? 1 : 0));
+    if (panel_sym) lower_valid_only = true;
   }
+  nbt_prev = 0;
   k1(n - 1, -1, 1);
   td_clean_kernel<T><<<h->num_sms * 4, 256, 0, st>>>(A, n);
   h->launches++;

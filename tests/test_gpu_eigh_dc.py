@@ -32,12 +32,13 @@ def _herm(rng, n, cplx):
     return X + X.conj().T
 
 
-@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("sym", ["0", "1", "100"])
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("n", [2, 3, 17, 64, 65, 130, 257, 600])
 def test_tridiag_and_backtransform(cplx, n, sym, monkeypatch):
-    # sym: force the lower-triangle-only (half-traffic) trailing matvec that large matrices use
-    monkeypatch.setenv("TNB_TD_SYM_MIN", "1" if sym else "0")
+    # sym: trailing size from which the lower-triangle-only (half-traffic) kernels are used -- 0: never,
+    # 1: always, 100: switch (and rebuild of the upper triangle) part-way through the reduction
+    monkeypatch.setenv("TNB_TD_SYM_MIN", sym)
     h, lib = _h()
     rng = np.random.default_rng(100 + n)
     A = _herm(rng, n, cplx)
