@@ -274,7 +274,18 @@ def run_gpu(args):
                 gather_mode = "all-gather fused into the step-4 GEMM epilogue (NVLink peer stores, device flag barrier)"
             except Exception as ex:   # noqa: BLE001
                 gather_mode = "nccl all-gather (peer mapping unavailable: %s)" % str(ex)[:80]
-        if fused is not None:
+        if args.shard == "mpo":
+            # the north star's MPO-bond split, for comparison (parallelism capped by w = 5)
+            Lfull2 = tn.DTensor(rnd(chi * chi * W), (chi, chi, W))
+            mpo = tn.shard.MpoSplitHeff(Lfull2, W1, W2, R)
+            gather_mode = "MPO-bond split: c-plane reduce to owners + all-reduce of H*phi (NCCL)"
+            fused = None
+
+            holder = {}
+
+            def step():
+                holder["out"] = mpo.apply(phi).data
+        elif fused is not None:
             def step():
                 fused.apply(L, W1, W2, R, phi)
         else:
@@ -342,8 +353,11 @@ def run_gpu(args):
             phi.data.copy_(ph, non_blocking=True)
             step()
             if rank == 0:
-                oh.copy_(fused.outs[(fused.epoch - 1) % len(fused.outs)].local() if fused is not None else gathered,
-                         non_blocking=True)
+                if args.shard == "mpo":
+                    src = holder["out"]
+                else:
+                    src = fused.outs[(fused.epoch - 1) % len(fused.outs)].local() if fused is not None else gathered
+                oh.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
     for _ in range(2):
         e2e_step()
@@ -387,7 +401,8 @@ def run_gpu(args):
             "config": {"workload": "C3 central-bond H_eff*phi (S=1/2 Heisenberg, N=100, maxdim 4096, d=2, w=5)",
                        "chi": chi, "d": D, "w": W, "flop_per_step": F,
                        "l2": "operands 0.5-2.7 GB per contraction, far larger than the 126 MB L2 (no flush needed)",
-                       "parallelism": "single GPU" if world == 1 else "output bond l' sharded x%d; %s" % (world, gather_mode)},
+                       "parallelism": "single GPU" if world == 1 else ("output bond l' sharded x%d; %s" % (world, gather_mode)
+                                                                       if args.shard == "lp" else "x%d; %s" % (world, gather_mode))},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": traffic, "kernel": "contract_kernel<f64, A K-major, B K-major, 16-byte copies, Cfg<64x128x16, warp 32x64, 3 stages, 2 CTA/SM>> (H_eff steps 1 and 4)",
                          "flop_per_launch": flops_per_launch, "ms_per_launch": kern_s * 1e3, "peak_source": peak_src},
@@ -415,6 +430,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chi", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="lp", choices=["lp", "mpo"],
+                    help="N>1: shard the output bond l' (default) or the MPO bond (north-star plan, for comparison)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: how the slabs of H*phi reach every rank")
     ap.add_argument("--no-sweep", action="store_true", help="skip the DMRG sweep-seconds sample (metric M1)")

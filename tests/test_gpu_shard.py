@@ -88,3 +88,58 @@ def test_heff_shard_fused_gather_two_gpus(cplx):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(e < 1e-12 for _, e in res)
+
+
+def _mpo_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from itensorsgpu_b200 import tn
+    rng = np.random.default_rng(53)
+    chi, cr, d, w = 48, 40, 2, 5
+    errs = []
+    for cplx in (False, True):
+        L = rand(rng, (chi, chi, w), cplx); R = rand(rng, (cr, cr, w), cplx)
+        W1 = rand(rng, (w, d, d, w), cplx); W2 = rand(rng, (w, d, d, w), cplx)
+        phi = rand(rng, (chi, d, d, cr), cplx)
+        D = tn.DTensor.from_numpy
+        ms = tn.shard.MpoSplitHeff(D(L), D(W1), D(W2), D(R))
+        out = ms.apply(D(phi))
+        errs.append(ot.rel_err(out.numpy(), od.heff_apply(L, W1, W2, R, phi)))
+    q.put((rank, max(errs)))
+    dist.destroy_process_group()
+
+
+def test_heff_mpo_bond_split_two_gpus():
+    """The north star's MPO-bond split (reduce of the c-planes + all-reduce of H*phi) against the oracle."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_mpo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(e < 1e-12 for _, e in res)
+
+
+def test_mpo_split_ranges():
+    from itensorsgpu_b200 import tn
+    assert tn.shard.mpo_split_ranges(5, 2) == [(0, 3), (3, 5)]
+    assert tn.shard.mpo_split_ranges(5, 8) == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 5), (5, 5), (5, 5)]
+    assert tn.shard.mpo_split_ranges(30, 8)[-1] == (27, 30)
