@@ -378,7 +378,7 @@ def run_gpu(args):
         ach = flops_per_launch / kern_s * 1e-12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cchi, _ = pick_cpu_chi(25.0, 2)
+            cchi, _ = pick_cpu_chi(45.0, 2)
             ctf, ctot = cpu_heff_tflops(cchi, 2, warm=0)
             cpu = {"value": ctf, "unit": UNIT, "cores": host_threads(), "kind": "port",
                    "sample": "oracle (NumPy/OpenBLAS dgemm) H_eff*phi at chi=%d, 2 applies, %.1f s" % (cchi, ctot)}

@@ -141,4 +141,45 @@ end
 # calls tnb_heff_apply; kept out of this file's executable part because ProjMPO internals differ between
 # ITensors 0.2.x patch releases -- see INTEGRATION.md for the call.
 
+# ---- TEBD gate in B form (right-canonical tensors in the Schmidt bases + Schmidt values): the unit of work of an
+# even/odd layer that can be spread over GPUs ([EXT] apply(gates, psi), examples/gate_evolution.jl:46)
+function tebd_gate_bform!(G::CuArray, lamL::CuVector{Float64}, B1::CuArray{ElT,3}, B2::CuArray{ElT,3};
+                          maxdim::Int=0, mindim::Int=1, cutoff::Float64=0.0) where {ElT}
+  chiL, d1, chiM = size(B1); _, d2, chiR = size(B2)
+  kmax = maxdim > 0 ? min(chiL * d1, d2 * chiR, maxdim) : min(chiL * d1, d2 * chiR)
+  b1 = CUDA.zeros(ElT, max(length(B1), chiL * d1 * kmax)); copyto!(b1, vec(B1))
+  b2 = CUDA.zeros(ElT, max(length(B2), kmax * d2 * chiR)); copyto!(b2, vec(B2))
+  lam = CUDA.zeros(Float64, kmax); nk = Ref{Int64}(0); err = Ref{Float64}(0.0)
+  check(ccall((:tnb_tebd_gate_bform, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+               Int64, Int64, Float64, Ptr{Cvoid}, Ref{Int64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), chiL, chiM, chiR, d1, d2, ptr(G), ptr(lamL), ptr(b1), ptr(b2),
+              maxdim, mindim, cutoff, ptr(lam), nk, err, stream()))
+  k = nk[]
+  return reshape(b1[1:chiL*d1*k], chiL, d1, k), reshape(b2[1:k*d2*chiR], k, d2, chiR), lam[1:k], err[]
+end
+
+# ---- multi-GPU: peer-mapped buffers and the slab GEMM with the all-gather fused into its epilogue.
+# One Julia process per GPU; exchange the 64-byte handles with MPI.jl / Distributed (host side only).
+function peer_alloc(nbytes::Integer)
+  p = Ref{Ptr{Cvoid}}(C_NULL); hd = zeros(UInt8, 64)
+  check(ccall((:tnb_peer_alloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}, Ptr{UInt8}), handle(), nbytes, p, hd))
+  return p[], hd
+end
+function peer_open(hd::Vector{UInt8})
+  p = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:tnb_peer_open, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Ptr{Cvoid}}), handle(), hd, p))
+  return p[]
+end
+# out_peers / flag_peers: Vector{Ptr{Cvoid}} of length world (own buffer included); epoch increases by one per call
+function heff_apply_shard_fused!(out_peers::Vector{Ptr{Cvoid}}, flag_peers::Vector{Ptr{Cvoid}}, epoch::Integer, rank::Integer,
+                                 d::BondDims, Lslab::CuArray, W1::CuArray, W2::CuArray, R::CuArray, phi::CuArray)
+  world = length(out_peers)
+  check(ccall((:tnb_heff_apply_shard_fused, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+               Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, UInt64, Ptr{Cvoid}),
+              handle(), dtype(eltype(phi)), Ref(d), rank, world, size(Lslab, 2), ptr(Lslab), ptr(W1), ptr(W2), ptr(R), ptr(phi),
+              out_peers, flag_peers, UInt64(epoch), stream()))
+end
+
 end # module
