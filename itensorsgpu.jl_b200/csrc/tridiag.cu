@@ -22,6 +22,23 @@ namespace tnb {
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// Programmatic dependent launch (sm_90+): the K1 -> K2 -> K1 ... chain of one column is latency-bound for n <= 4096,
+// so each kernel is launched with programmaticStreamSerialization: its blocks are scheduled while the previous
+// kernel drains, run whatever does not depend on it, and block in pdl_wait() until it has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 constexpr int TD_NB = 64;        // panel width of the reduction
 constexpr int TD_NBT = 256;      // reflectors per block in the back-transformation
 
@@ -50,6 +67,7 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
   __shared__ T bc[2];
   __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();            // the K2 of this column may be scheduled; it waits for this grid to complete
   const long long nrows = n - i;
   T alpha2 = a_zero<T>(), tau_p = a_zero<T>();
   const T* vprev = ZL + (size_t)(jp < 0 ? 0 : jp) * ldz;
@@ -66,6 +84,14 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
   }
   const bool fin = (warp == 0 && active);
   const T a_in = (fin && do_column) ? A[r + (size_t)i * n] : a_zero<T>();
+  T zi_v = a_zero<T>(), zi_w = a_zero<T>(), zi_v2 = a_zero<T>(), zi_w2 = a_zero<T>();   // row i of the panel (warp 0)
+  if (warp == 0 && jp > 0) {
+    if (lane < jp) { zi_v = ZL[i + (size_t)lane * ldz]; zi_w = ZL[i + (size_t)(nb + lane) * ldz]; }
+    if (lane + 32 < jp) { zi_v2 = ZL[i + (size_t)(lane + 32) * ldz]; zi_w2 = ZL[i + (size_t)(nb + lane + 32) * ldz]; }
+  }
+  if (jp >= 0) tau_p = tau[i - 1];
+  // everything above was written before the previous column's K2 started; what follows is K2's output
+  pdl_wait();
   const T vp = (fin && jp >= 0) ? vprev[r] : a_zero<T>();
   // y of the previous column: either final values (K2) or the per-tile slots of the symmetric matvec (K2S),
   // which are summed here in a fixed order (warp w takes slots w, w+8, ...)
@@ -81,13 +107,7 @@ __global__ void __launch_bounds__(256) td_k1_kernel(typename ElemT<CPLX>::T* __r
       for (int k = lane; k < nbt; k += 32) y0 = a_add(y0, P[(size_t)k * TS]);
     }
   }
-  T zi_v = a_zero<T>(), zi_w = a_zero<T>(), zi_v2 = a_zero<T>(), zi_w2 = a_zero<T>();   // row i of the panel (warp 0)
-  if (warp == 0 && jp > 0) {
-    if (lane < jp) { zi_v = ZL[i + (size_t)lane * ldz]; zi_w = ZL[i + (size_t)(nb + lane) * ldz]; }
-    if (lane + 32 < jp) { zi_v2 = ZL[i + (size_t)(lane + 32) * ldz]; zi_w2 = ZL[i + (size_t)(nb + lane + 32) * ldz]; }
-  }
   if (jp >= 0) {
-    tau_p = tau[i - 1];
     // y^H v: fixed-order sum of K2's per-CTA partials
     T part = a_zero<T>();
     for (int b = tid; b < nparts; b += 256) part = a_add(part, yparts[b]);
@@ -245,6 +265,8 @@ __global__ void __launch_bounds__(TD_K2T, 2) td_k2_kernel(const typename ElemT<C
   __shared__ T wsum[NW];
   T* xs = (T*)k2_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();               // K1 of this column must have completed (scal, the updated column, the finalised w)
+  pdl_trigger();            // ... after which the next column's K1 may start its independent loads
   const long long r0 = i + 1;
   const int nt = (int)(n - r0);
   const T sc = scal[0];
@@ -387,6 +409,8 @@ __global__ void __launch_bounds__(256, CPLX ? 2 : 3) td_k2s_kernel(const typenam
   __shared__ T yvred[4];
   __shared__ T rowacc[8][TS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_trigger();
   const long long r0 = i + 1;
   const int nt = (int)(n - r0);
   const T sc = scal[0];
@@ -524,8 +548,10 @@ static int launch_k2(Handle* h, const typename ElemT<CPLX>::T* A, int64_t n, int
   int grid = std::min((tasks + NW - 1) / NW, h->num_sms * 2);
   if (grid < 1) grid = 1;
   const size_t smem = (size_t)(nt + 2) * sizeof(T);
-  if (smem <= 96 * 1024) td_k2_kernel<CPLX, CW, true><<<grid, TD_K2T, smem, st>>>(A, n, i, j, ZL, ZR, ldz, scal, ybuf, yparts);
-  else td_k2_kernel<CPLX, CW, false><<<grid, TD_K2T, 0, st>>>(A, n, i, j, ZL, ZR, ldz, scal, ybuf, yparts);
+  if (smem <= 96 * 1024)
+    launch_pdl(td_k2_kernel<CPLX, CW, true>, dim3(grid), dim3(TD_K2T), smem, st, true, A, (long long)n, (long long)i, j, ZL, ZR, (long long)ldz, scal, ybuf, yparts);
+  else
+    launch_pdl(td_k2_kernel<CPLX, CW, false>, dim3(grid), dim3(TD_K2T), 0, st, true, A, (long long)n, (long long)i, j, ZL, ZR, (long long)ldz, scal, ybuf, yparts);
   h->launches++;
   return grid;
 }
@@ -568,8 +594,8 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
   const double one[2] = {1.0, 0.0}, mone[2] = {-1.0, 0.0};
   auto k1 = [&](int64_t i, int jp, int do_column) {
     const int grid = (int)((n - i + 31) / 32);
-    td_k1_kernel<CPLX><<<grid, 256, 0, st>>>(A, n, i, jp, do_column, ZL, ZR, n, ybuf, yparts, nparts, P, nbt_prev, tau, d, e, scal,
-                                             h->partials, h->counter);
+    launch_pdl(td_k1_kernel<CPLX>, dim3(grid), dim3(256), 0, st, true, A, (long long)n, (long long)i, jp, do_column, ZL, ZR, (long long)n,
+               (const T*)ybuf, (const T*)yparts, nparts, (const T*)P, nbt_prev, tau, d, e, scal, h->partials, h->counter);
     h->launches++;
   };
   for (int64_t p0 = 0; p0 < n - 1; p0 += nb) {
@@ -593,7 +619,8 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
       if (panel_sym) {
         const int nbt = (nt + TD_TS - 1) / TD_TS;
         const int ntiles = nbt * (nbt + 1) / 2;
-        td_k2s_kernel<CPLX><<<ntiles + (2 * j + 7) / 8, 256, 0, st>>>(A, n, i, j, ZL, ZR, n, scal, P, nbt, ntiles, ybuf, yparts);
+        launch_pdl(td_k2s_kernel<CPLX>, dim3(ntiles + (2 * j + 7) / 8), dim3(256), 0, st, true, (const T*)A, (long long)n, (long long)i, j, ZL, ZR,
+                   (long long)n, (const T*)scal, P, nbt, ntiles, ybuf, yparts);
         nparts = ntiles;
         nbt_prev = nbt;
         h->launches++;
