@@ -206,8 +206,11 @@ def sweep_sample(tn, chi, branch):
     for o in ("left", "right"):
         for b in range(N - 1):
             key = (o, D100[b], D100[b + 2])
+            other = ("right" if o == "left" else "left", D100[b], D100[b + 2])
             if key in tshape:
                 est += tshape[key]
+            elif other in tshape:       # the very first bond's callback also holds the environment build: use the return pass
+                est += tshape[other]
             else:
                 missing += 1
     full = [tshape.get((o, chi, chi)) for o in ("left", "right")]
