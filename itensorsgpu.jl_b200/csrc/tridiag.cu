@@ -396,7 +396,7 @@ __device__ __forceinline__ double ld_stream(const double* p) {
 __device__ __forceinline__ double2 ld_stream(const double2* p) { return ld_stream16(p); }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(256, CPLX ? 2 : 3) td_k2s_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i, int j,
+__global__ void __launch_bounds__(256, 2) td_k2s_kernel(const typename ElemT<CPLX>::T* __restrict__ A, long long n, long long i, int j,
                                                       typename ElemT<CPLX>::T* ZL, typename ElemT<CPLX>::T* ZR, long long ldz,
                                                       const typename ElemT<CPLX>::T* __restrict__ scal,
                                                       typename ElemT<CPLX>::T* __restrict__ P, int nbt, int ntiles,
@@ -456,9 +456,10 @@ __global__ void __launch_bounds__(256, CPLX ? 2 : 3) td_k2s_kernel(const typenam
 #pragma unroll
   for (int q = 0; q < 4; ++q) { vr[q] = vI[lane + 32 * q]; yr[q] = a_zero<T>(); rok[q] = (I * TS + lane + 32 * q) < nt; }
   const T* base = A + (r0 + (size_t)I * TS + lane) + (size_t)(r0 + (size_t)J * TS) * n;
-#pragma unroll 1
-  for (int cb = 0; cb < TS / 8; cb += CB) {
-    T av[CB][4];
+  // two-stage software pipeline: the loads of column batch b+1 are in flight while batch b is reduced
+  constexpr int NBATCH = (TS / 8) / CB;
+  T av[2][CB][4];
+  auto load_batch = [&](int cb, T (*dst)[4]) {
 #pragma unroll
     for (int u = 0; u < CB; ++u) {
       const int c = warp + 8 * (cb + u);
@@ -467,18 +468,23 @@ __global__ void __launch_bounds__(256, CPLX ? 2 : 3) td_k2s_kernel(const typenam
       for (int q = 0; q < 4; ++q) {
         bool ok = cok && rok[q];
         if (diag) ok = ok && (lane + 32 * q >= c);
-        av[u][q] = ok ? ld_stream(base + 32 * q + (size_t)c * n) : a_zero<T>();
+        dst[u][q] = ok ? ld_stream(base + 32 * q + (size_t)c * n) : a_zero<T>();
       }
     }
+  };
+  load_batch(0, av[0]);
+#pragma unroll
+  for (int bt = 0; bt < NBATCH; ++bt) {
+    if (bt + 1 < NBATCH) load_batch((bt + 1) * CB, av[(bt + 1) & 1]);
 #pragma unroll
     for (int u = 0; u < CB; ++u) {
-      const int c = warp + 8 * (cb + u);
+      const int c = warp + 8 * (bt * CB + u);
       const T vc = vJ[c];
       T s = a_zero<T>();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        s = a_add(s, a_cmul(av[u][q], vr[q]));
-        if (!diag || (lane + 32 * q > c)) yr[q] = a_add(yr[q], a_mul(av[u][q], vc));
+        s = a_add(s, a_cmul(av[bt & 1][u][q], vr[q]));
+        if (!diag || (lane + 32 * q > c)) yr[q] = a_add(yr[q], a_mul(av[bt & 1][u][q], vc));
       }
       s = a_warp_sum(s);
       if (lane == 0) colres[c] = s;
