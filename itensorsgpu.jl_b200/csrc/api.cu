@@ -107,6 +107,7 @@ int tnb_destroy(tnb_handle_t h) {
   if (H->counter) cudaFree(H->counter);
   if (H->what) cudaFree(H->what);
   if (H->scal_host) cudaFreeHost(H->scal_host);
+  for (auto& e : H->ev) if (e) cudaEventDestroy(e);
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
   delete H;
   return TNB_OK;

@@ -627,14 +627,16 @@ int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32
                           nullptr, nullptr, 0);
 }
 
-// strideC (optional): element stride of every C mode (C is then a strided window of a larger tensor);
+// strideA / strideB / strideC (optional): element stride of every mode (the operand is then a strided window
+// of a larger tensor);
 // peerC/npeer (optional): the epilogue stores every output element to ALL npeer base pointers (peer-mapped
 // buffers of the other GPUs included) instead of C -- the all-gather of a sharded result fused into the GEMM.
 int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
                      const void* A, int nB, const int64_t* extB, const int32_t* modeB,
                      const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
                      const void* alpha, const void* beta, int flags, cudaStream_t st,
-                     const int64_t* strideC, void* const* peerC, int npeer) {
+                     const int64_t* strideC, void* const* peerC, int npeer, const int64_t* strideA,
+                     const int64_t* strideB) {
   if (npeer < 0 || npeer > TNB_MAX_PEERS) return set_err(h, TNB_ERR_BAD_ARG, "contract: npeer %d", npeer);
   if (npeer > 0 && beta) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: beta with peer stores");
   if (dtype != TNB_F64 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: dtype %d", dtype);
@@ -650,7 +652,7 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
   for (int i = 0; i < nA; ++i) {
     if (find(modeA[i])) return set_err(h, TNB_ERR_BAD_ARG, "contract: repeated mode %d in A", modeA[i]);
     if (extA[i] < 1) return set_err(h, TNB_ERR_BAD_ARG, "contract: extent < 1 in A");
-    recs.push_back({modeA[i], extA[i], s, 0, 0, i, -1, -1});
+    recs.push_back({modeA[i], extA[i], strideA ? strideA[i] : s, 0, 0, i, -1, -1});
     s *= extA[i];
   }
   s = 1;
@@ -660,9 +662,9 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
     ModeRec* r = find(modeB[i]);
     if (r) {
       if (r->ext != extB[i]) return set_err(h, TNB_ERR_DIM_MISMATCH, "contract: mode %d has extent %lld in A, %lld in B", modeB[i], r->ext, (long long)extB[i]);
-      r->sB = s; r->posB = i;
+      r->sB = strideB ? strideB[i] : s; r->posB = i;
     } else {
-      recs.push_back({modeB[i], extB[i], 0, s, 0, -1, i, -1});
+      recs.push_back({modeB[i], extB[i], 0, strideB ? strideB[i] : s, 0, -1, i, -1});
     }
     s *= extB[i];
   }

@@ -538,6 +538,86 @@ int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
 }
 
 size_t heff_workspace_bytes(int dtype, const tnb_bond_dims* d) { return heff_ws_bytes(dtype, d); }
+// Host-buffer H_eff*phi with the PCIe copies hidden behind the two big GEMMs: phi is uploaded in NC chunks over r
+// (its slowest mode) on the copy stream while step 1 already contracts the chunks that have arrived (each chunk's
+// T1 slice is a strided window, r being a middle mode of T1); steps 2+3 run once; step 4 is cut over r' (a
+// strided window of R, a contiguous chunk of the result) and every finished chunk starts its download while the
+// next one is being computed.  Exposed copy time: one chunk each way instead of the whole vector twice.
+static int heff_host_pipelined(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
+                               const void* W2, const void* R, const void* phi_host, void* out_host, void* dphi,
+                               void* dout, void* t0, void* t1, cudaStream_t st) {
+  const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
+  const size_t es = elsize(dtype);
+  const size_t nb = (size_t)cl * cr * d1 * d2 * es;
+  const int NC = (cr >= 1024) ? 4 : 1;
+  if (NC == 1) {
+    TNB_CUDA(h, cudaMemcpyAsync(dphi, phi_host, nb, cudaMemcpyHostToDevice, st));
+    TNB_TRY(heff_core(h, dtype, d, cl, L, W1, W2, R, dphi, dout, t0, t1, st));
+    TNB_CUDA(h, cudaMemcpyAsync(out_host, dout, nb, cudaMemcpyDeviceToHost, st));
+    return check_cuda(h, cudaStreamSynchronize(st), "heff_apply_host sync");
+  }
+  for (int i = 0; i < 2 * NC + 1; ++i)
+    if (!h->ev[i]) TNB_CUDA(h, cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  cudaStream_t cs = h->copy_stream;
+  // the copy stream must not run ahead of work already queued on `st` that still uses dphi / dout
+  TNB_CUDA(h, cudaEventRecord(h->ev[2 * NC], st));
+  TNB_CUDA(h, cudaStreamWaitEvent(cs, h->ev[2 * NC], 0));
+  const int64_t rc = (cr + NC - 1) / NC;
+  const size_t slab = (size_t)cl * d1 * d2;                 // elements of phi per unit of r
+  for (int c = 0; c < NC; ++c) {
+    const int64_t r0 = c * rc, r1 = std::min<int64_t>(cr, r0 + rc);
+    if (r1 <= r0) continue;
+    TNB_CUDA(h, cudaMemcpyAsync((char*)dphi + r0 * slab * es, (const char*)phi_host + r0 * slab * es, (r1 - r0) * slab * es,
+                                cudaMemcpyHostToDevice, cs));
+    TNB_CUDA(h, cudaEventRecord(h->ev[c], cs));
+  }
+  for (int c = 0; c < NC; ++c) {       // 1. T1[s1,s2,r in chunk,l',a] = phi[l,s1,s2,r in chunk] L[l,l',a]
+    const int64_t r0 = c * rc, r1 = std::min<int64_t>(cr, r0 + rc);
+    if (r1 <= r0) continue;
+    TNB_CUDA(h, cudaStreamWaitEvent(st, h->ev[c], 0));
+    int64_t ea[] = {cl, d1, d2, r1 - r0}; int32_t ma[] = {mL, mS1, mS2, mR};
+    int64_t eb[] = {cl, cl, wl};          int32_t mb[] = {mL, mLp, mA};
+    int64_t ec[] = {d1, d2, r1 - r0, cl, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
+    int64_t sc[] = {1, d1, d1 * d2, d1 * d2 * cr, d1 * d2 * cr * cl};
+    TNB_TRY(contract_impl_ex(h, dtype, 4, ea, ma, (const char*)dphi + r0 * slab * es, 3, eb, mb, L, 5, ec, mc,
+                             (char*)t0 + (size_t)r0 * d1 * d2 * es, nullptr, nullptr, 0, st, sc, nullptr, 0));
+  }
+  const void* T3 = t0;
+  if (heff23_fused(h, dtype, d, cl, W1, W2, t0, t1, h->what, st)) {
+    TNB_TRY(check_cuda(h, cudaGetLastError(), "heff23"));
+    T3 = t1;
+  } else {
+    {
+      int64_t ea[] = {d1, d2, cr, cl, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
+      int64_t eb[] = {wl, d1, d1, wm};     int32_t mb[] = {mA, mS1, mS1p, mB};
+      int64_t ec[] = {d2, cr, cl, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W1, 5, ec, mc, t1, nullptr, nullptr, 0, st));
+    }
+    {
+      int64_t ea[] = {d2, cr, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
+      int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
+      int64_t ec[] = {cr, cl, d1, d2, wr}; int32_t mc[] = {mR, mLp, mS1p, mS2p, mC};
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 4, eb, mb, W2, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+    }
+  }
+  for (int c = 0; c < NC; ++c) {       // 4. out[l',s1',s2',r' in chunk] = T3 R[r, r' in chunk, c]
+    const int64_t r0 = c * rc, r1 = std::min<int64_t>(cr, r0 + rc);
+    if (r1 <= r0) continue;
+    int64_t ea[] = {cr, cl, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t eb[] = {cr, r1 - r0, wr};    int32_t mb[] = {mR, mRp, mC};
+    int64_t sb[] = {1, cr, cr * cr};
+    int64_t ec[] = {cl, d1, d2, r1 - r0}; int32_t mc[] = {mLp, mS1p, mS2p, mRp};
+    TNB_TRY(contract_impl_ex(h, dtype, 5, ea, ma, T3, 3, eb, mb, (const char*)R + (size_t)r0 * cr * es, 4, ec, mc,
+                             (char*)dout + r0 * slab * es, nullptr, nullptr, 0, st, nullptr, nullptr, 0, nullptr, sb));
+    TNB_CUDA(h, cudaEventRecord(h->ev[NC + c], st));
+    TNB_CUDA(h, cudaStreamWaitEvent(cs, h->ev[NC + c], 0));
+    TNB_CUDA(h, cudaMemcpyAsync((char*)out_host + r0 * slab * es, (const char*)dout + r0 * slab * es, (r1 - r0) * slab * es,
+                                cudaMemcpyDeviceToHost, cs));
+  }
+  TNB_CUDA(h, cudaStreamSynchronize(cs));
+  return check_cuda(h, cudaStreamSynchronize(st), "heff_apply_host sync");
+}
+
 int heff_core_pub(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1, const void* W2,
                   const void* R, const void* phi, void* out, void* t0, void* t1, cudaStream_t st) {
   return heff_core(h, dtype, d, d->chiL, L, W1, W2, R, phi, out, t0, t1, st);
@@ -636,11 +716,7 @@ int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, co
   TNB_TRY(ws_alloc(H, hw / 2, &t1));
   TNB_TRY(ws_alloc(H, nb, &dphi));
   TNB_TRY(ws_alloc(H, nb, &dout));
-  TNB_CUDA(H, cudaMemcpyAsync(dphi, phi_host, nb, cudaMemcpyHostToDevice, ST));
-  TNB_TRY(heff_core_pub(H, dtype, dims, L, W1, W2, R, dphi, dout, t0, t1, ST));
-  TNB_CUDA(H, cudaMemcpyAsync(out_host, dout, nb, cudaMemcpyDeviceToHost, ST));
-  TNB_CUDA(H, cudaStreamSynchronize(ST));
-  return TNB_OK;
+  return heff_host_pipelined(H, dtype, dims, L, W1, W2, R, phi_host, out_host, dphi, dout, t0, t1, ST);
 }
 
 int tnb_env_update_left(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d, int32_t wL,

@@ -64,6 +64,7 @@ struct Handle {
   double* partials = nullptr;   // per-block partial sums for reductions (8192 doubles)
   unsigned* counter = nullptr;  // last-block-done ticket (self-resetting)
   void* what = nullptr;         // combined two-site MPO matrix of the fused H_eff step 2+3 (64 KB)
+  cudaEvent_t ev[16] = {};      // chunk hand-over events of the pipelined host-buffer H_eff (created on first use)
 };
 constexpr int RED_MAX_BLOCKS = 1024;
 
@@ -96,7 +97,8 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
                      const void* A, int nB, const int64_t* extB, const int32_t* modeB,
                      const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
                      const void* alpha, const void* beta, int flags, cudaStream_t st,
-                     const int64_t* strideC, void* const* peerC, int npeer);
+                     const int64_t* strideC, void* const* peerC, int npeer, const int64_t* strideA = nullptr,
+                     const int64_t* strideB = nullptr);
 // plain column-major GEMM helper built on the same kernel:
 //   C[m x n] (ldc) <- alpha * op(A) * op(B) + beta * C ; op = N / T / C(onj-transpose)
 int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,

@@ -31,17 +31,22 @@ def test_heff_apply(cplx, shape):
     assert ot.rel_err(got, od.heff_apply(L, W1, W2, R, phi)) < 1e-12
 
 
-def test_heff_apply_host_buffers():
+@pytest.mark.parametrize("shape", [(48, 40, 2, 5, False), (40, 1030, 2, 5, False), (24, 1024, 3, 5, True)])
+def test_heff_apply_host_buffers(shape):
+    """chiR >= 1024 takes the pipelined form: phi uploaded in chunks over r that overlap step 1 (strided T1
+    windows), H*phi downloaded in chunks over r' that overlap step 4 (strided windows of R); 1030 is ragged."""
     import torch
     from itensorsgpu_b200 import tn
     rng = np.random.default_rng(32)
-    cl, cr, d, w = 48, 40, 2, 5
-    L, W1, W2, R, phi = _random_bond(rng, cl, cr, d, w, False)
+    cl, cr, d, w, cplx = shape
+    L, W1, W2, R, phi = _random_bond(rng, cl, cr, d, w, cplx)
     ph = torch.from_numpy(np.ascontiguousarray(phi.ravel(order="F"))).pin_memory()
     out = torch.empty_like(ph).pin_memory()
-    tn.ops.heff_apply_host(dev(L), dev(W1), dev(W2), dev(R), ph, out, (cl, d, d, cr))
-    got = out.numpy().reshape((cl, d, d, cr), order="F")
-    assert ot.rel_err(got, od.heff_apply(L, W1, W2, R, phi)) < 1e-12
+    for _ in range(2):                   # twice: the second call reuses the events and the copy stream
+        out.zero_()
+        tn.ops.heff_apply_host(dev(L), dev(W1), dev(W2), dev(R), ph, out, (cl, d, d, cr))
+        got = out.numpy().reshape((cl, d, d, cr), order="F")
+        assert ot.rel_err(got, od.heff_apply(L, W1, W2, R, phi)) < 1e-12
 
 
 @pytest.mark.parametrize("cplx", [False, True])
