@@ -250,3 +250,22 @@ def test_dmrg_strict_parity_fast_eigensolver(route, monkeypatch):
     assert abs(e - e_ref) < 1e-10
     for t in psi.cpu().tensors[1:]:
         assert omps.right_orthogonality_error(t) < 1e-11
+
+
+def test_dmrg_config_c1_full_size():
+    """BASELINE.json configs[0] at full size: S=1 Heisenberg chain, N=100, 5 sweeps maxdim 10/20/100/100/200,
+    cutoff 1e-11 (examples/dmrg.jl's model with ITensors.jl's stock schedule).  Energies after identical sweeps
+    within the north star's 1e-10 of the CPU path on every sweep, and the known ground-state energy of the
+    N=100 open S=1 chain (-138.940086) reached."""
+    from itensorsgpu_b200 import tn
+    N = 100
+    Ws = models.heisenberg_mpo(N, 1.0)
+    psi0 = omps.random_mps(N, 3, 10, np.random.default_rng(2024))
+    kw = dict(maxdim=[10, 20, 100, 100, 200], cutoff=1e-11)
+    e_ref, _, hist_ref = od.dmrg(Ws, psi0, od.Sweeps(5, **kw))
+    hist = []
+    e, psi = tn.dmrg(tn.cu(_host_mpo(tn, Ws)), tn.cu(_host_mps(tn, psi0)), tn.Sweeps(5, **kw),
+                     observer=lambda sw, b, o, en, err: hist.append(en) if (o == "right" and b == 0) else None)
+    assert np.max(np.abs(np.array(hist) - np.array(hist_ref))) < 1e-10
+    assert abs(e - e_ref) < 1e-10
+    assert abs(e - (-138.940086)) < 2e-6
