@@ -440,21 +440,10 @@ __global__ void __launch_bounds__(256, 2) td_k2s_kernel(const typename ElemT<CPL
   while (I * (I + 1) / 2 > (int)blockIdx.x) --I;
   const int J = (int)blockIdx.x - I * (I + 1) / 2;
   const bool diag = (I == J);
-  if (tid < TS) {
-    const T v = vat(I * TS + tid);
-    vI[tid] = v;
-    if (diag && I * TS + tid < nt) {
-      ZL[r0 + I * TS + tid + (size_t)j * ldz] = v;
-      ZR[r0 + I * TS + tid + (size_t)(nb + j) * ldz] = v;
-    }
-  } else {
-    vJ[tid - TS] = vat(J * TS + tid - TS);
-  }
-  __syncthreads();
   T vr[4], yr[4];
   bool rok[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { vr[q] = vI[lane + 32 * q]; yr[q] = a_zero<T>(); rok[q] = (I * TS + lane + 32 * q) < nt; }
+  for (int q = 0; q < 4; ++q) { yr[q] = a_zero<T>(); rok[q] = (I * TS + lane + 32 * q) < nt; }
   const T* base = A + (r0 + (size_t)I * TS + lane) + (size_t)(r0 + (size_t)J * TS) * n;
   // two-stage software pipeline: the loads of column batch b+1 are in flight while batch b is reduced
   constexpr int NBATCH = (TS / 8) / CB;
@@ -472,7 +461,20 @@ __global__ void __launch_bounds__(256, 2) td_k2s_kernel(const typename ElemT<CPL
       }
     }
   };
-  load_batch(0, av[0]);
+  load_batch(0, av[0]);      // the matrix stream starts before the (dependent-latency) fetch of the two v segments
+  if (tid < TS) {
+    const T v = vat(I * TS + tid);
+    vI[tid] = v;
+    if (diag && I * TS + tid < nt) {
+      ZL[r0 + I * TS + tid + (size_t)j * ldz] = v;
+      ZR[r0 + I * TS + tid + (size_t)(nb + j) * ldz] = v;
+    }
+  } else {
+    vJ[tid - TS] = vat(J * TS + tid - TS);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) vr[q] = vI[lane + 32 * q];
 #pragma unroll
   for (int bt = 0; bt < NBATCH; ++bt) {
     if (bt + 1 < NBATCH) load_batch((bt + 1) * CB, av[(bt + 1) & 1]);
