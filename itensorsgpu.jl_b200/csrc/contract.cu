@@ -18,6 +18,7 @@
 #include <array>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace tnb {
 
@@ -458,6 +459,89 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------
+// small-K / small-N contractions (K, N <= 32, M huge): H_eff steps 2 and 3 issued as separate contractions
+// (K = w d = 10), the middle step of the environment updates, gate application (K = N = d^2).  These are pure
+// HBM streaming (read A once, write C once), and the DMMA tile kernel wastes most of its 64x128x16 tile on them
+// (1.0 TB/s).  Here one thread owns one m: it loads its K values of A (registers), B sits zero-padded in shared
+// memory as [n][k] so that a k-pair is one broadcast LDS.128, and every n is one coalesced store across the warp.
+// ------------------------------------------------------------------------------------
+template <bool CPLX, int KB>
+__global__ void __launch_bounds__(256) smallk_kernel(const __grid_constant__ GemmParams p) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  __shared__ __align__(16) T Bs[32 * KB];
+  __shared__ long long koffA[KB], noffC[32];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 32 * KB; e += 256) {
+    const int n = e / KB, k = e % KB;
+    T v;
+    if constexpr (CPLX) v = make_double2(0.0, 0.0); else v = 0.0;
+    if (n < p.N && k < p.K) {
+      v = ((const T*)p.B)[decode<true>(p.gk, k) + decode<false>(p.gn, n)];
+      if constexpr (CPLX) { if (p.conjB) v.y = -v.y; }
+    }
+    Bs[e] = v;
+  }
+  if (tid < KB) koffA[tid] = tid < p.K ? decode<false>(p.gk, tid) : -1;
+  if (tid >= 32 && tid < 64) noffC[tid - 32] = (tid - 32) < p.N ? decode<true>(p.gn, tid - 32) : 0;
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * 256 + tid;
+  if (m >= p.M) return;
+  const T* Ap = (const T*)p.A + decode<false>(p.gm, (int)m);
+  T* Cp = (T*)p.C + decode<true>(p.gm, (int)m);
+  T a[KB];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) {
+    if constexpr (CPLX) a[k] = make_double2(0.0, 0.0); else a[k] = 0.0;
+    if (koffA[k] >= 0) {
+      a[k] = Ap[koffA[k]];
+      if constexpr (CPLX) { if (p.conjA) a[k].y = -a[k].y; }
+    }
+  }
+  const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
+  for (int n = 0; n < p.N; ++n) {
+    const T* bn = Bs + n * KB;
+    if constexpr (!CPLX) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < KB; k += 2) {
+        const double2 b2 = *reinterpret_cast<const double2*>(bn + k);
+        acc = fma(a[k], b2.x, acc);
+        acc = fma(a[k + 1], b2.y, acc);
+      }
+      double v = p.alpha_re * acc;
+      if (has_beta) v += p.beta_re * Cp[noffC[n]];
+      Cp[noffC[n]] = v;
+    } else {
+      double xr = 0.0, xi = 0.0;
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const double2 b = bn[k];
+        xr += a[k].x * b.x - a[k].y * b.y;
+        xi += a[k].x * b.y + a[k].y * b.x;
+      }
+      double2 v = make_double2(p.alpha_re * xr - p.alpha_im * xi, p.alpha_re * xi + p.alpha_im * xr);
+      if (has_beta) {
+        const double2 o = Cp[noffC[n]];
+        v.x += p.beta_re * o.x - p.beta_im * o.y;
+        v.y += p.beta_re * o.y + p.beta_im * o.x;
+      }
+      Cp[noffC[n]] = v;
+    }
+  }
+}
+
+template <bool CPLX>
+static int launch_smallk(Handle* h, GemmParams& p, cudaStream_t st) {
+  const unsigned grid = (unsigned)(((long long)p.M + 255) / 256);
+  if (p.K <= 4) smallk_kernel<CPLX, 4><<<grid, 256, 0, st>>>(p);
+  else if (p.K <= 8) smallk_kernel<CPLX, 8><<<grid, 256, 0, st>>>(p);
+  else if (p.K <= 16) smallk_kernel<CPLX, 16><<<grid, 256, 0, st>>>(p);
+  else smallk_kernel<CPLX, 32><<<grid, 256, 0, st>>>(p);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "smallk_kernel launch");
+}
+
+// ------------------------------------------------------------------------------------
 // host side: launch
 // ------------------------------------------------------------------------------------
 // Two independent 4-warp CTAs per SM: their barrier / copy phases drift apart, so one CTA's
@@ -529,6 +613,12 @@ static bool all_even(const long long* s, int from, int n) {
 // Decide per-operand staging direction and copy width, pick a tile config, launch.
 static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) {
   const bool cplx = dtype == TNB_C128;
+  {  // small-K / small-N streaming form
+    static const bool off = getenv("TNB_SMALLK") && !strcmp(getenv("TNB_SMALLK"), "off");
+    if (!off && p.K <= 32 && p.N <= 32 && p.M >= 16384 && p.batch <= 1 && !p.boffA && !p.boffB && !p.boffC && !p.splitN &&
+        p.npeer == 0 && !p.lowerOnly)
+      return cplx ? launch_smallk<true>(h, p, st) : launch_smallk<false>(h, p, st);
+  }
   // A: contiguous along K if the first K mode has unit stride in A; along M if the first M mode has.
   bool ak, bk;
   int va = 1, vb = 1;

@@ -139,3 +139,26 @@ def test_error_codes():
         tn.ops.contract(A, ("i", "j"), B, ("j", "k"))
     with pytest.raises(tn.TnbError):
         tn.ops.contract(A, ("i", "i"), B, ("j", "k"))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_small_k_streaming_form(cplx):
+    """K, N <= 32 with a huge M takes the HBM-streaming kernel (one thread per m): H_eff steps 2 / 3 issued as
+    separate contractions (SURVEY 8d shape iii), the middle step of an environment update, gate application;
+    with output permutations, alpha/beta, conj flags and ragged (odd) extents."""
+    rng = np.random.default_rng(1240)
+    chi, d, w = 96, 2, 5
+    dims = dict(s1=d, s2=d, r=chi, lp=chi, a=w, s1p=d, b=w, s2p=d, c=w, l=chi + 1, x=131, y=129, g1=d, g2=d)
+    # H_eff step 2 and step 3 (K = w d = 10, N = d w = 10, M = d chi^2 = 18432)
+    check_contract(rng, dims, ("s1", "s2", "r", "lp", "a"), ("a", "s1", "s1p", "b"), cplx, TOL, lc=("s2", "r", "lp", "s1p", "b"))
+    check_contract(rng, dims, ("s2", "r", "lp", "s1p", "b"), ("b", "s2", "s2p", "c"), cplx, TOL, lc=("r", "lp", "s1p", "s2p", "c"))
+    # environment-update middle step: T1[l',a,s,r] W[a,s,s',b]
+    check_contract(rng, dims, ("lp", "a", "s1", "r"), ("a", "s1", "s1p", "b"), cplx, TOL, lc=("lp", "s1p", "b", "r"))
+    # gate application: theta[l,s1,s2,r] G[g1,g2,s1,s2] (K = N = 4), odd extents, conj and alpha/beta
+    check_contract(rng, dims, ("x", "s1", "s2", "y"), ("g1", "g2", "s1", "s2"), cplx, TOL, lc=("x", "g1", "g2", "y"))
+    check_contract(rng, dims, ("x", "s1", "s2", "y"), ("g1", "g2", "s1", "s2"), cplx, TOL, lc=("g2", "x", "y", "g1"),
+                   alpha=0.7 - (0.2j if cplx else 0.0), beta=-1.3, conj_a=cplx, conj_b=cplx)
+    # K = 1 (outer-product-like) and N = 1 (matrix-vector-like) edges of the same form
+    d2 = dict(m=20000, k=1, n=7, kk=9)
+    check_contract(rng, d2, ("m", "k"), ("k", "n"), cplx, TOL)
+    check_contract(rng, d2, ("kk", "m"), ("kk",), cplx, TOL)
