@@ -12,5 +12,5 @@ from ._lib import TnbError, DimensionMismatch, handle, load  # noqa: F401
 from .ops import DTensor  # noqa: F401
 from .itensor import (Index, ITensor, cu, cpu, cuITensor, randomCuITensor, prime, dag, noprime, norm, dot, permute,  # noqa: F401
                       svd, eigen, qr, davidson, commonind, delta)
-from .mps import (MPS, MPO, Sweeps, dmrg, apply, inner, orthogonalize, cuMPS, cuMPO, randomCuMPS, productCuMPS,  # noqa: F401
+from .mps import (MPS, MPO, Sweeps, dmrg, apply, inner, orthogonalize, add, truncate, contract, cuMPS, cuMPO, randomCuMPS, productCuMPS,  # noqa: F401
                   randomCuMPO, heisenberg_mpo, tfim_mpo)

@@ -173,6 +173,72 @@ def orthogonalize(psi, j):
     return MPS(ts, llim=j - 1, rlim=j + 1)
 
 
+# ---- MPS / MPO algebra on the same kernels ([EXT] ITensors `+`, `truncate!`, `contract(::MPO, ::MPS)`;
+#      the reference exercises them in test/test_cumpo.jl:42-173 and test/test_cumps.jl:196-246)
+def add(psi, phi):
+    """|psi> + |phi>: direct sum of the bond spaces (exact; follow with ``truncate``).  Block placement only."""
+    if not (psi.on_gpu and phi.on_gpu):
+        raise _lib.TnbError(3, "add: move both MPS to the GPU with cu(); there is no CPU path")
+    N = len(psi)
+    if len(phi) != N:
+        raise _lib.DimensionMismatch(2, "add: MPS lengths differ")
+    out = []
+    for j in range(N):
+        A, B = psi.tensors[j], phi.tensors[j]
+        l1, d, r1 = A.dims
+        l2, d2, r2 = B.dims
+        if d != d2:
+            raise _lib.DimensionMismatch(2, "add: site dimension differs at site %d" % j)
+        dt = torch.complex128 if torch.complex128 in (A.dtype, B.dtype) else torch.float64
+        L = l1 if j == 0 else l1 + l2
+        R = r1 if j == N - 1 else r1 + r2
+        if (j == 0 and l1 != l2) or (j == N - 1 and r1 != r2):
+            raise _lib.DimensionMismatch(2, "add: boundary bond dimensions differ")
+        C = torch.zeros(R, d, L, dtype=dt, device=A.data.device)           # row-major (R,d,L) == column-major [L,d,R]
+        lo_l, lo_r = (0 if j == 0 else l1), (0 if j == N - 1 else r1)
+        C[:r1, :, :l1] = A.data.view(r1, d, l1)
+        C[lo_r:lo_r + r2, :, lo_l:lo_l + l2] = B.data.view(r2, d, l2)
+        out.append(DTensor(C.reshape(-1), (L, d, R)))
+    return MPS(out)
+
+
+def truncate(psi, maxdim=None, cutoff=None):
+    """[EXT] ``truncate!(psi; maxdim, cutoff)``: orthogonalise to the last site, then split every bond by a
+    truncated SVD on the way back.  Returns a right-canonical MPS (centre at site 0)."""
+    if not psi.on_gpu:
+        raise _lib.TnbError(3, "truncate: move psi to the GPU with cu(); there is no CPU path")
+    N = len(psi)
+    ts = list(orthogonalize(psi, N - 1).tensors)
+    Cc = ts[N - 1]
+    for j in range(N - 1, 0, -1):
+        l, d, r = Cc.dims
+        A, B, _ = ops.factorize_bond(DTensor(Cc.data, (l, 1, d, r)), ortho="right", which_decomp="svd", maxdim=maxdim,
+                                     cutoff=cutoff or 0.0)
+        k = B.dims[0]
+        ts[j] = B
+        Cc, _ = ops.contract(ts[j - 1], ("a", "s", "l"), DTensor(A.data, (l, k)), ("l", "k"), lc=("a", "s", "k"))
+    ts[0] = Cc
+    return MPS(ts, llim=-1, rlim=1)
+
+
+def contract(H, psi, maxdim=None, cutoff=None):
+    """[EXT] ``contract(H::MPO, psi::MPS; maxdim, cutoff)`` = H|psi> as an MPS: site-wise product
+    B[(l a), s', (r b)] = sum_s W[a,s,s',b] A[l,s,r] (one contraction per site), then ``truncate``."""
+    if not (H.on_gpu and psi.on_gpu):
+        raise _lib.TnbError(3, "contract: move H and psi to the GPU with cu(); there is no CPU path")
+    if len(H) != len(psi):
+        raise _lib.DimensionMismatch(2, "contract: MPO and MPS lengths differ")
+    out = []
+    for W, A in zip(H.tensors, psi.tensors):
+        T, _ = ops.contract(A, ("l", "s", "r"), W, ("a", "s", "u", "b"), lc=("l", "a", "u", "r", "b"))
+        l, a, u, r, b = T.dims
+        out.append(DTensor(T.data, (l * a, u, r * b)))
+    res = MPS(out)
+    if maxdim is None and cutoff is None:
+        return res
+    return truncate(res, maxdim=maxdim, cutoff=cutoff)
+
+
 class Sweeps:
     """[EXT] ``Sweeps(n)`` + ``maxdim!/mindim!/cutoff!/noise!`` (``examples/dmrg.jl:20-24``)."""
 
@@ -191,10 +257,73 @@ class Sweeps:
         return self.nsweep
 
 
-def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None):
+class _EnvCache:
+    """Left/right environments of a sweep ([EXT] ProjMPO's LR cache filled by makeL!/makeR!).  ``store="device"``
+    keeps every environment in HBM (C3: 99 x 640 MiB at chi = 4096).  ``store="host"`` keeps only the ones about
+    to be used on the device: each new environment is copied to pinned host memory on a side stream and dropped,
+    and the next one a sweep direction will need is prefetched one bond ahead, so the PCIe traffic (one
+    environment each way per bond) hides behind the bond step.  Needed when N * w * chi^2 * 16 B exceeds HBM
+    (C5: 16 GB per environment at chi = 8192, w = 30)."""
+
+    def __init__(self, N, store="device"):
+        if store not in ("device", "host"):
+            raise _lib.TnbError(1, "env_store must be 'device' or 'host'")
+        self.store = store
+        self.dev = [None] * N          # DTensor on the device (or None)
+        self.host = [None] * N         # (pinned tensor, dims) when offloaded
+        self.ready = [None] * N        # event: prefetch finished
+        self.side = torch.cuda.Stream() if store == "host" else None
+
+    def put(self, j, t):
+        self.dev[j] = t
+        if self.store == "host" and t.size > 1:
+            buf = torch.empty(t.data.shape, dtype=t.data.dtype, pin_memory=True)
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                buf.copy_(t.data, non_blocking=True)
+            t.data.record_stream(self.side)
+            self.host[j] = (buf, t.dims)
+
+    def drop(self, j):
+        """forget environment j entirely (it is stale)"""
+        self.dev[j] = None
+        self.host[j] = None
+        self.ready[j] = None
+
+    def evict(self, j):
+        """keep only the host copy of environment j"""
+        if self.store == "host" and self.host[j] is not None:
+            self.dev[j] = None
+
+    def prefetch(self, j):
+        if self.store != "host" or j < 0 or j >= len(self.dev) or self.dev[j] is not None or self.host[j] is None:
+            return
+        buf, dims = self.host[j]
+        with torch.cuda.stream(self.side):
+            d = torch.empty(buf.shape, dtype=buf.dtype, device="cuda")
+            d.copy_(buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.dev[j] = DTensor(d, dims)
+        self.ready[j] = ev
+
+    def get(self, j):
+        if self.dev[j] is None:
+            self.prefetch(j)
+        if self.ready[j] is not None:
+            torch.cuda.current_stream().wait_event(self.ready[j])
+            self.dev[j].data.record_stream(torch.cuda.current_stream())
+            self.ready[j] = None
+        if self.dev[j] is None:
+            raise _lib.TnbError(1, "environment %d is not available" % j)
+        return self.dev[j]
+
+
+def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None, env_store="device"):
     """``energy, psi = dmrg(H, psi0, sweeps)`` ([EXT] ITensors 0.2 two-site DMRG; reference call sites
     ``examples/dmrg.jl:25``, ``test/dmrg.jl:27,75``).  Per bond: ONE fused C call (phi = A1*A2, Lanczos with
-    krylovdim matvecs, optional noise term, truncated factorization) plus one environment update."""
+    krylovdim matvecs, optional noise term, truncated factorization) plus one environment update.
+    ``env_store="host"`` spills the environment cache to pinned host memory (see ``_EnvCache``)."""
     if not (H.on_gpu and psi0.on_gpu):
         raise _lib.TnbError(3, "dmrg: move H and psi0 to the GPU with cu(); there is no CPU path")
     N = len(psi0)
@@ -207,32 +336,40 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
     ts = [t.astype(dt) for t in ts]
     Ws = [w.astype(dt) for w in Ws]
     one = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1, 1))
-    Rs = [None] * N
-    Rs[N - 1] = one
+    Rs = _EnvCache(N, env_store)
+    Ls = _EnvCache(N, env_store)
+    Rs.put(N - 1, one)
     for j in range(N - 1, 1, -1):
-        Rs[j - 1] = ops.env_update_right(Rs[j], ts[j], Ws[j])
-    Ls = [None] * N
-    Ls[0] = one
+        Rs.put(j - 1, ops.env_update_right(Rs.get(j), ts[j], Ws[j]))
+        if j < N - 1:
+            Rs.evict(j)
+    Ls.put(0, one)
     energy = None
     for sw in range(sweeps.nsweep):
         kw = dict(maxdim=sweeps.maxdim[sw], mindim=sweeps.mindim[sw], cutoff=sweeps.cutoff[sw],
                   noise=sweeps.noise[sw], krylovdim=krylovdim, maxiter=maxiter, which_decomp=which_decomp)
         maxerr = 0.0
         for b in range(0, N - 1):
-            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls[b], Ws[b], Ws[b + 1], Rs[b + 1], ts[b], ts[b + 1],
+            Rs.prefetch(b + 2)                      # the next bond's right environment, one bond ahead
+            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls.get(b), Ws[b], Ws[b + 1], Rs.get(b + 1), ts[b], ts[b + 1],
                                                                "left", **kw)
-            Ls[b + 1] = ops.env_update_left(Ls[b], ts[b], Ws[b])
+            Ls.put(b + 1, ops.env_update_left(Ls.get(b), ts[b], Ws[b]))
             if b + 1 < N - 1:
-                Rs[b + 1] = None      # stale now (site b+1 changed); freeing it keeps one environment per bond resident
+                Rs.drop(b + 1)        # stale now (site b+1 changed): one environment per bond stays alive
+            if b > 0:
+                Ls.evict(b)
             maxerr = max(maxerr, err)
             if observer:
                 observer(sw, b, "left", energy, err)
         for b in range(N - 2, -1, -1):
-            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls[b], Ws[b], Ws[b + 1], Rs[b + 1], ts[b], ts[b + 1],
+            Ls.prefetch(b - 1)
+            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls.get(b), Ws[b], Ws[b + 1], Rs.get(b + 1), ts[b], ts[b + 1],
                                                                "right", **kw)
-            Rs[b] = ops.env_update_right(Rs[b + 1], ts[b + 1], Ws[b + 1])
+            Rs.put(b, ops.env_update_right(Rs.get(b + 1), ts[b + 1], Ws[b + 1]))
             if b > 0:
-                Ls[b] = None
+                Ls.drop(b)
+            if b + 1 < N - 1:
+                Rs.evict(b + 1)
             maxerr = max(maxerr, err)
             if observer:
                 observer(sw, b, "right", energy, err)

@@ -103,3 +103,54 @@ def to_dense(psi):
     for A in psi[1:]:
         T = np.tensordot(T, A, axes=(T.ndim - 1, 0))
     return T.reshape(T.shape[1:-1])
+
+
+# ---- MPS / MPO algebra ([EXT] ITensors `+`, `truncate!`, `contract(::MPO, ::MPS)`; pinned by the reference's
+#      consistency tests test/test_cumpo.jl:42-173 and test/test_cumps.jl:196-246)
+def add(psi, phi):
+    """|psi> + |phi> as an MPS (direct sum of the bond spaces, exact)."""
+    N = len(psi)
+    out = []
+    for j in range(N):
+        A, B = psi[j], phi[j]
+        l1, d, r1 = A.shape
+        l2, _, r2 = B.shape
+        if j == 0:
+            C = np.concatenate([A, B], axis=2)
+        elif j == N - 1:
+            C = np.concatenate([A, B], axis=0)
+        else:
+            C = np.zeros((l1 + l2, d, r1 + r2), dtype=np.result_type(A, B))
+            C[:l1, :, :r1] = A
+            C[l1:, :, r1:] = B
+        out.append(C)
+    return out
+
+
+def truncate(psi, maxdim=None, cutoff=None):
+    """[EXT] truncate!(psi): orthogonalise to the last site, then SVD-split every bond on the way back.
+    Returns a right-canonical MPS (centre at site 0)."""
+    psi = orthogonalize(psi, len(psi) - 1)
+    N = len(psi)
+    C = psi[N - 1]
+    for j in range(N - 1, 0, -1):
+        l, d, r = C.shape
+        Lm, Rm, _ = linalg.factorize(C.reshape(l, d * r, order="F"), ortho="right", which_decomp="svd", maxdim=maxdim,
+                                     cutoff=cutoff)
+        k = Rm.shape[0]
+        psi[j] = Rm.reshape(k, d, r, order="F")
+        C = np.tensordot(psi[j - 1], Lm, axes=(2, 0))
+    psi[0] = C
+    return psi
+
+
+def contract_mpo_mps(Ws, psi, maxdim=None, cutoff=None):
+    """H|psi> as an MPS: site-wise product B[(l a), s', (r b)] = sum_s W[a,s,s',b] A[l,s,r], then truncate."""
+    out = []
+    for W, A in zip(Ws, psi):
+        T = np.einsum("asub,lsr->laurb", W, A)
+        l, a, u, r, b = T.shape
+        out.append(T.reshape(l * a, u, r * b, order="F"))
+    if maxdim is None and cutoff is None:
+        return out
+    return truncate(out, maxdim=maxdim, cutoff=cutoff)

@@ -269,3 +269,58 @@ def test_dmrg_config_c1_full_size():
     assert np.max(np.abs(np.array(hist) - np.array(hist_ref))) < 1e-10
     assert abs(e - e_ref) < 1e-10
     assert abs(e - (-138.940086)) < 2e-6
+
+
+def test_dmrg_environment_offload_is_transparent():
+    """env_store="host" (environment cache spilled to pinned host memory, prefetched one bond ahead) must give
+    bit-identical energies to the all-in-HBM cache: it only moves data."""
+    from itensorsgpu_b200 import tn
+    N = 14
+    Ws = _generic_heisenberg(N)
+    psi0 = omps.random_mps(N, 2, 4, np.random.default_rng(8))
+    kw = dict(maxdim=[8, 16, 24], cutoff=1e-12, noise=[1e-9, 0.0, 0.0])
+    runs = []
+    for store in ("device", "host"):
+        hist = []
+        e, psi = tn.dmrg(tn.cu(_host_mpo(tn, Ws)), tn.cu(_host_mps(tn, psi0)), tn.Sweeps(3, **kw), env_store=store,
+                         observer=lambda sw, b, o, en, err: hist.append(en))
+        runs.append((e, hist, [t.numpy() for t in psi.tensors]))
+    assert runs[0][0] == runs[1][0]
+    assert runs[0][1] == runs[1][1]
+    assert all(np.array_equal(a, b) for a, b in zip(runs[0][2], runs[1][2]))
+    with pytest.raises(tn.TnbError):
+        tn.dmrg(tn.cu(_host_mpo(tn, Ws)), tn.cu(_host_mps(tn, psi0)), tn.Sweeps(1, maxdim=4), env_store="disk")
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_mps_algebra_add_truncate_contract(cplx):
+    """[EXT] `+`, `truncate!`, `contract(::MPO, ::MPS)` on the GPU kernels vs the oracle / dense algebra, and the
+    reference's consistency relation inner(phi, contract(H, psi)) == inner(phi, H, psi)
+    (test/test_cumpo.jl:89-99,131; test/test_cumps.jl:196-246)."""
+    from itensorsgpu_b200 import tn
+    rng = np.random.default_rng(62)
+    N = 8
+    dt = np.complex128 if cplx else np.float64
+    psi = omps.random_mps(N, 2, 6, rng, dtype=dt)
+    phi = omps.random_mps(N, 2, 5, rng, dtype=dt)
+    Ws = models.heisenberg_mpo(N, 0.5)
+    gpsi, gphi, gH = tn.cu(_host_mps(tn, psi)), tn.cu(_host_mps(tn, phi)), tn.cu(_host_mpo(tn, Ws))
+    dpsi, dphi = omps.to_dense(psi), omps.to_dense(phi)
+    s = tn.add(gpsi, gphi)
+    assert np.linalg.norm(omps.to_dense(s.cpu().tensors) - (dpsi + dphi)) < 1e-12
+    t = tn.truncate(tn.add(gpsi, gpsi), cutoff=1e-14)
+    assert t.maxlinkdim() <= 6 and np.linalg.norm(omps.to_dense(t.cpu().tensors) - 2 * dpsi) < 1e-11
+    for tens in t.cpu().tensors[1:]:
+        assert omps.right_orthogonality_error(tens) < 1e-12
+    tm = tn.truncate(s, maxdim=4)
+    ref = omps.truncate(omps.add(psi, phi), maxdim=4)
+    assert ot.rel_err(omps.to_dense(tm.cpu().tensors), omps.to_dense(ref)) < 1e-9
+    Hpsi = tn.contract(gH, gpsi)
+    assert np.linalg.norm(omps.to_dense(Hpsi.cpu().tensors) - omps.to_dense(omps.contract_mpo_mps(Ws, psi))) < 1e-11
+    lhs, rhs = tn.inner(gphi, Hpsi), tn.inner(gphi, gpsi, gH)
+    assert abs(lhs - rhs) < 1e-11 * max(1.0, abs(rhs))
+    Ht = tn.contract(gH, gpsi, maxdim=8, cutoff=1e-13)
+    assert Ht.maxlinkdim() <= 8
+    assert ot.rel_err(omps.to_dense(Ht.cpu().tensors), omps.to_dense(omps.contract_mpo_mps(Ws, psi, maxdim=8, cutoff=1e-13))) < 1e-9
+    with pytest.raises(tn.DimensionMismatch):
+        tn.add(gpsi, tn.cu(tn.MPS(psi[:-1])))

@@ -217,3 +217,25 @@ def test_bform_tebd_matches_sequential_apply(cplx):
     a, b = omps.to_dense(Bs), omps.to_dense(ref)
     a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
     assert np.linalg.norm(a - b) < 10 * np.sqrt(max(e0, e1, 1e-30))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_mps_algebra_restatement(cplx):
+    """add / truncate / contract(MPO, MPS) of the oracle against dense linear algebra (the reference's own
+    consistency checks: test/test_cumpo.jl:53,89,99,131; test/test_cumps.jl:196-246)."""
+    from oracle import models, mps as omps
+    rng = np.random.default_rng(61)
+    N = 8
+    dt = np.complex128 if cplx else np.float64
+    psi = omps.random_mps(N, 2, 6, rng, dtype=dt)
+    phi = omps.random_mps(N, 2, 5, rng, dtype=dt)
+    Ws = models.heisenberg_mpo(N, 0.5)
+    dpsi, dphi = omps.to_dense(psi), omps.to_dense(phi)
+    assert np.linalg.norm(omps.to_dense(omps.add(psi, phi)) - (dpsi + dphi)) < 1e-13
+    assert np.linalg.norm(omps.to_dense(omps.truncate(omps.add(psi, psi))) - 2 * dpsi) < 1e-12     # rank stays that of psi
+    assert max(t.shape[2] for t in omps.truncate(omps.add(psi, psi), cutoff=1e-14)[:-1]) <= 6
+    Hpsi = omps.contract_mpo_mps(Ws, psi)
+    assert abs(omps.inner(phi, Hpsi) - np.vdot(dphi, omps.to_dense(Hpsi))) < 1e-12
+    assert abs(omps.inner(psi, Hpsi) - omps.expect_mpo(psi, Ws)) < 1e-12 * max(1.0, abs(omps.expect_mpo(psi, Ws)))
+    tr = omps.contract_mpo_mps(Ws, psi, maxdim=8)
+    assert max(t.shape[2] for t in tr[:-1]) <= 8
