@@ -99,6 +99,16 @@ int tnb_permute_axpby(tnb_handle_t h, int dtype, int n, const int64_t* extA,
                       const int32_t* modeA, const void* A, const int32_t* modeB, void* B,
                       const void* alpha, const void* beta, void* stream);
 
+/* C[modeC] <- A[modeA] * diag[index of scaled_mode]   (modeC a permutation of modeA)
+ * Contraction of a dense tensor with a Diag tensor over one of the Diag's two indices: a scale along that mode
+ * (the caller relabels the mode to the Diag's other index; modeC carries the NDTensors output order).  diag:
+ * device vector of extent(scaled_mode) elements of diag_dtype (TNB_F64 for the S of svd / D of eigen).
+ * Replaces the Diag x Dense contractions of src/tensor/cudiag.jl:105-161, which densify the diagonal
+ * (zero-fill + scatter, :147-157) and run a full dense contraction. */
+int tnb_diag_contract(tnb_handle_t h, int dtype, int n, const int64_t* extA, const int32_t* modeA, const void* A,
+                      int32_t scaled_mode, const void* diag, int diag_dtype, const int32_t* modeC, void* C,
+                      void* stream);
+
 /* x <- alpha * x       (scalar * and /: src/tensor/cudense.jl:22,502) */
 int tnb_scale(tnb_handle_t h, int dtype, int64_t n, void* x, const void* alpha, void* stream);
 

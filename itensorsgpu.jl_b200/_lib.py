@@ -50,6 +50,7 @@ SIGNATURES = {
     "tnb_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp,
                             _vp, _vp, _int, _vp]),
     "tnb_permute_axpby": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _pi32, _vp, _vp, _vp, _vp]),
+    "tnb_diag_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _i32, _vp, _int, _pi32, _vp, _vp]),
     "tnb_scale": (_int, [_vp, _int, _i64, _vp, _vp, _vp]),
     "tnb_dot": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tnb_nrm2": (_int, [_vp, _int, _i64, _vp, _vp, _pdbl, _vp]),

@@ -140,6 +140,13 @@ int tnb_permute_axpby(tnb_handle_t h, int dtype, int n, const int64_t* extA, con
   return permute_axpby_impl(H, dtype, n, extA, modeA, A, modeB, B, alpha, beta, ST);
 }
 
+int tnb_diag_contract(tnb_handle_t h, int dtype, int n, const int64_t* extA, const int32_t* modeA, const void* A,
+                      int32_t scaled_mode, const void* diag, int diag_dtype, const int32_t* modeC, void* C, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!extA || !modeA || !modeC) return set_err(H, TNB_ERR_BAD_ARG, "diag_contract: null pointer");
+  return diag_contract_impl(H, dtype, n, extA, modeA, A, scaled_mode, diag, diag_dtype, modeC, C, (cudaStream_t)stream);
+}
+
 int tnb_scale(tnb_handle_t h, int dtype, int64_t n, void* x, const void* alpha, void* stream) {
   if (!h) return TNB_ERR_BAD_ARG;
   return scale_impl(H, dtype, n, x, alpha, ST);

@@ -118,6 +118,9 @@ int permute_axpby_impl(Handle* h, int dtype, int n, const int64_t* extA, const i
                        const void* A, const int32_t* modeB, void* B, const void* alpha,
                        const void* beta, cudaStream_t st);
 int scale_impl(Handle* h, int dtype, int64_t n, void* x, const void* alpha, cudaStream_t st);
+int diag_contract_impl(Handle* h, int dtype, int n, const int64_t* extA, const int32_t* modeA, const void* A,
+                       int32_t scaled_mode, const void* diag, int diag_dtype, const int32_t* modeC, void* C,
+                       cudaStream_t st);
 int dot_impl(Handle* h, int dtype, int64_t n, const void* x, const void* y, void* result_dev,
              cudaStream_t st);
 int nrm2_impl(Handle* h, int dtype, int64_t n, const void* x, double* result_dev,

@@ -233,6 +233,55 @@ int permute_axpby_impl(Handle* h, int dtype, int n, const int64_t* extA, const i
   return check_cuda(h, cudaGetLastError(), "permute_axpby launch");
 }
 
+// ------------------------------------------------------------------------------------
+// Diag x Dense: out[e] = A[e] * d[(e / inner) % ext]  -- the contraction of a dense tensor with a Diag tensor over
+// one of the Diag's two indices is a scale along that mode (plus a relabel, and a permutation when the
+// NDTensors output order moves the mode).  The reference densifies the diagonal and runs a full contraction
+// (src/tensor/cudiag.jl:147-161): an n x n zero-fill + scatter + GEMM for what is one streaming pass.
+// ------------------------------------------------------------------------------------
+template <typename T, typename DT>
+__global__ void __launch_bounds__(256) scale_mode_kernel(T* __restrict__ out, const T* __restrict__ in, long long total,
+                                                          long long inner, long long ext, const DT* __restrict__ d) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const DT f = d[(e / inner) % ext];
+    const T v = in[e];
+    if constexpr (sizeof(T) == 16 && sizeof(DT) == 16) out[e] = make_double2(v.x * f.x - v.y * f.y, v.x * f.y + v.y * f.x);
+    else if constexpr (sizeof(T) == 16) out[e] = make_double2(v.x * f, v.y * f);
+    else out[e] = v * f;
+  }
+}
+
+int diag_contract_impl(Handle* h, int dtype, int n, const int64_t* extA, const int32_t* modeA, const void* A,
+                       int32_t scaled_mode, const void* diag, int diag_dtype, const int32_t* modeC, void* C,
+                       cudaStream_t st) {
+  if (dtype != TNB_F64 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "diag_contract: dtype %d", dtype);
+  if (diag_dtype == TNB_C128 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "diag_contract: complex diagonal with a real tensor");
+  if (n < 1 || n > 64 || !A || !C || !diag) return set_err(h, TNB_ERR_BAD_ARG, "diag_contract: bad argument");
+  long long inner = 1, ext = -1, total = 1;
+  bool same = true;
+  for (int i = 0; i < n; ++i) {
+    if (extA[i] < 1) return set_err(h, TNB_ERR_BAD_ARG, "diag_contract: extent < 1");
+    if (modeA[i] == scaled_mode) { ext = extA[i]; inner = total; }
+    total *= extA[i];
+    if (modeC[i] != modeA[i]) same = false;
+  }
+  if (ext < 0) return set_err(h, TNB_ERR_BAD_ARG, "diag_contract: mode %d is not a mode of A", scaled_mode);
+  const bool cplx = dtype == TNB_C128;
+  void* dst = C;
+  if (!same) {
+    ws_reset(h);
+    TNB_TRY(ws_alloc(h, (size_t)total * elsize(dtype), &dst));
+  }
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)h->num_sms * 16));
+  if (!cplx) scale_mode_kernel<double, double><<<grid, 256, 0, st>>>((double*)dst, (const double*)A, total, inner, ext, (const double*)diag);
+  else if (diag_dtype == TNB_C128) scale_mode_kernel<double2, double2><<<grid, 256, 0, st>>>((double2*)dst, (const double2*)A, total, inner, ext, (const double2*)diag);
+  else scale_mode_kernel<double2, double><<<grid, 256, 0, st>>>((double2*)dst, (const double2*)A, total, inner, ext, (const double*)diag);
+  h->launches++;
+  TNB_TRY(check_cuda(h, cudaGetLastError(), "scale_mode launch"));
+  if (!same) TNB_TRY(permute_axpby_impl(h, dtype, n, extA, modeA, dst, modeC, C, nullptr, nullptr, st));
+  return TNB_OK;
+}
+
 int scale_impl(Handle* h, int dtype, int64_t n, void* x, const void* alpha, cudaStream_t st) {
   if (!alpha) return TNB_OK;
   int32_t mode = 0;

@@ -62,13 +62,35 @@ class Spectrum:
         self.truncerr = truncerr
 
 
+class DiagStore:
+    """Diagonal storage ([EXT] NDTensors ``Diag``; GPU form ``src/tensor/cudiag.jl``): a rank-2 ITensor whose only
+    non-zero entries are ``vec[j]`` at (j, j).  ``vec``: 1-D torch CUDA tensor.  This is what ``svd`` returns for S
+    and ``eigen`` for D on the CPU path; contracting it with a dense tensor is a scale along one mode
+    (``tnb_diag_contract``), not a GEMM with a densified k x k matrix."""
+
+    def __init__(self, vec):
+        self.vec = vec
+
+    @property
+    def dtype(self):
+        return self.vec.dtype
+
+    def dense(self):
+        k = self.vec.numel()
+        return DTensor(torch.diag(self.vec).reshape(-1).contiguous(), (k, k))
+
+
 class ITensor:
-    """Dense ITensor.  ``store`` is a DTensor (GPU, ``CuDense``) or a NumPy array (CPU container)."""
+    """ITensor.  ``store`` is a DTensor (GPU dense, ``CuDense``), a DiagStore (GPU diagonal) or a NumPy array
+    (CPU container)."""
 
     def __init__(self, store, inds):
         self.inds = tuple(inds)
         dims = tuple(i.dim for i in self.inds)
-        if isinstance(store, DTensor):
+        if isinstance(store, DiagStore):
+            if len(dims) != 2 or dims[0] != dims[1] or dims[0] != store.vec.numel():
+                raise _lib.DimensionMismatch(2, "Diag storage of length %d for indices of dims %s" % (store.vec.numel(), dims))
+        elif isinstance(store, DTensor):
             if store.dims != dims:
                 store = DTensor(store.data, dims)
         else:
@@ -80,15 +102,21 @@ class ITensor:
     # ---- placement
     @property
     def on_gpu(self):
-        return isinstance(self.store, DTensor)
+        return isinstance(self.store, (DTensor, DiagStore))
+
+    @property
+    def is_diag(self):
+        return isinstance(self.store, DiagStore)
 
     def _dev(self):
         if not self.on_gpu:
             raise _lib.TnbError(3, "arithmetic on a CPU ITensor: move it with cu(); there is no CPU path")
-        return self.store
+        return self.store.dense() if self.is_diag else self.store
 
     def array(self):
         """Logical ndarray on the host (``array(cpu(A))``)."""
+        if self.is_diag:
+            return np.diag(self.store.vec.cpu().numpy())
         return self.store.numpy() if self.on_gpu else np.array(self.store)
 
     def scalar(self):
@@ -109,14 +137,32 @@ class ITensor:
         return ITensor(self.store, [m.get(i, i) for i in self.inds])
 
     def dag(self):
+        if self.is_diag:
+            return ITensor(DiagStore(torch.conj_physical(self.store.vec)), self.inds)
         s = self._dev()
         if s.dtype == torch.complex128:
             return ITensor(DTensor(torch.conj_physical(s.data), s.dims), self.inds)
         return self
 
     # ---- arithmetic: every op is one C-ABI call
+    def _diag_times_dense(self, o, diag_first):
+        """self: Diag (u, v); o: dense sharing exactly one of u, v.  Output order = NDTensors' (first operand's free
+        indices, then the second's): one scale-along-a-mode pass (+ a permute when the mode moves)."""
+        u, v = self.inds
+        shared = u if u in o.inds else v
+        other = v if shared == u else u
+        free = [i for i in o.inds if i != shared]
+        out_inds = ([other] + free) if diag_first else (free + [other])
+        lc = [shared if i == other else i for i in out_inds]          # labels of the kernel: the relabel is host-side
+        C = ops.diag_contract(o.store, o.inds, shared, self.store.vec, lc)
+        return ITensor(C, out_inds)
+
     def __mul__(self, o):
         if isinstance(o, ITensor):
+            if self.on_gpu and o.on_gpu and (self.is_diag != o.is_diag):            # cudiag.jl:105-161 without densifying
+                dg, dn = (self, o) if self.is_diag else (o, self)
+                if sum(i in dn.inds for i in dg.inds) == 1:
+                    return dg._diag_times_dense(dn, diag_first=self.is_diag)
             C, lc = ops.contract(self._dev(), self.inds, o._dev(), o.inds)        # contract!! (cudense.jl:83-110)
             return ITensor(C, lc)
         out = self._dev().clone()
@@ -244,14 +290,14 @@ def _matricize(A, Linds):
 
 def svd(A, Linds, **kw):
     """``U,S,V,spec = svd(A, Linds...; maxdim, mindim, cutoff)`` with ``A ~ U*S*V`` (CPU convention;
-    GPU body replaced: ``src/tensor/culinearalgebra.jl:33-72``).  S is a diagonal ITensor (dense here)."""
+    GPU body replaced: ``src/tensor/culinearalgebra.jl:33-72``).  S is a Diag-storage ITensor."""
     M, L, R = _matricize(A, Linds)
     U, S, V, err = ops.svd(M, **kw)
     k = U.dims[1]
     u, v = Index(k, "Link,u"), Index(k, "Link,v")
     Ut = ITensor(DTensor(U.data, tuple(i.dim for i in L) + (k,)), L + (u,))
     Vt = ITensor(DTensor(V.data, tuple(i.dim for i in R) + (k,)), R + (v,))
-    St = ITensor(DTensor(torch.diag(S.to(A._dev().dtype)).reshape(-1).contiguous(), (k, k)), (u, v))
+    St = ITensor(DiagStore(S), (u, v))            # Diag storage, as on the CPU path (the reference's GPU path densifies)
     return Ut, St, Vt, Spectrum((S ** 2).cpu().numpy(), err)
 
 
@@ -265,7 +311,7 @@ def eigen(A, Linds, Rinds, **kw):
     k = U.dims[1]
     l, r = Index(k, "Link,eigen"), Index(k, "Link,eigen")
     Ut = ITensor(DTensor(U.data, tuple(i.dim for i in Rinds) + (k,)), tuple(Rinds) + (r,))
-    Dt = ITensor(DTensor(torch.diag(D.to(A._dev().dtype)).reshape(-1).contiguous(), (k, k)), (l, r))
+    Dt = ITensor(DiagStore(D), (l, r))            # Diag(real(D)), as culinearalgebra.jl:106 / the CPU path
     return Dt, Ut, Spectrum(D.cpu().numpy(), err)
 
 

@@ -481,3 +481,26 @@ def tebd_gate_bform(G, lamL, B1, B2, maxdim=None, mindim=1, cutoff=0.0):
                                       _ptr(lam), C.byref(nk), C.byref(err), _stream()))
     k = nk.value
     return DTensor(b1[: m * k], (cl, d1, k)), DTensor(b2[: k * n], (k, d2, cr)), lam[:k], err.value
+
+
+def diag_contract(A, la, mode, diag, lc):
+    """C[lc] <- A[la] * diag[index of ``mode``]  (``lc`` a permutation of ``la``; ``tnb_diag_contract``):
+    the contraction of a dense tensor with a Diag tensor over one of its two indices.  ``diag``: 1-D torch CUDA
+    tensor (float64, or complex128 with a complex A)."""
+    h = _lib.handle()
+    la, lc = list(la), list(lc)
+    if len(la) != len(lc) or set(la) != set(lc):
+        raise _lib.TnbError(1, "diag_contract: output labels must be a permutation of the input labels")
+    if mode not in la:
+        raise _lib.TnbError(1, "diag_contract: %r is not a mode of A" % (mode,))
+    if diag.numel() != A.dims[la.index(mode)]:
+        raise _lib.DimensionMismatch(2, "diag_contract: diagonal of length %d for a mode of extent %d" %
+                                     (diag.numel(), A.dims[la.index(mode)]))
+    if diag.dtype == torch.complex128 and A.dtype != torch.complex128:
+        A = A.astype(torch.complex128)
+    ids = {l: i for i, l in enumerate(la)}
+    out = DTensor.empty(tuple(A.dims[la.index(l)] for l in lc), A.dtype, A.data.device)
+    diag = diag.contiguous()
+    h.check(h.lib.tnb_diag_contract(h.h, _dt(A.data), len(la), _i64(A.dims), _i32([ids[l] for l in la]), _ptr(A.data),
+                                    ids[mode], _ptr(diag), _dt(diag), _i32([ids[l] for l in lc]), _ptr(out.data), _stream()))
+    return out

@@ -120,3 +120,48 @@ def test_truncate_matches_cpu_rule_randomised():
         assert got[2] == want[2], (trial, kw, got, want)
         assert got[0] == pytest.approx(want[0], rel=1e-12, abs=1e-300)
         assert got[1] == pytest.approx(want[1], rel=1e-12, abs=1e-300)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_diag_contract_and_diag_storage(cplx):
+    """Diag x Dense as a scale along one mode (tnb_diag_contract) instead of the reference's densify + full
+    contraction (src/tensor/cudiag.jl:105-161), and the Diag-storage S / D that svd / eigen return on the CPU
+    path (a12, a13, a16); checked against plain dense algebra."""
+    import torch
+    from itensorsgpu_b200 import tn
+    rng = np.random.default_rng(71)
+    A = rand(rng, (5, 7, 6), cplx)
+    dvec = rng.standard_normal(7)
+    # raw entry point: same order, and with an output permutation
+    out = tn.ops.diag_contract(dev(A), ("i", "j", "k"), "j", torch.from_numpy(dvec).cuda(), ("i", "j", "k")).numpy()
+    assert np.array_equal(out, A * dvec[None, :, None])
+    out = tn.ops.diag_contract(dev(A), ("i", "j", "k"), "j", torch.from_numpy(dvec).cuda(), ("j", "k", "i")).numpy()
+    assert np.array_equal(out, (A * dvec[None, :, None]).transpose(1, 2, 0))
+    if cplx:
+        cvec = dvec + 1j * rng.standard_normal(7)
+        out = tn.ops.diag_contract(dev(A), ("i", "j", "k"), "j", torch.from_numpy(cvec).cuda(), ("k", "i", "j")).numpy()
+        assert np.allclose(out, (A * cvec[None, :, None]).transpose(2, 0, 1), rtol=1e-15, atol=0)
+    with pytest.raises(tn.TnbError):
+        tn.ops.diag_contract(dev(A), ("i", "j", "k"), "x", torch.from_numpy(dvec).cuda(), ("i", "j", "k"))
+    # ITensor level: svd returns Diag S; U*S, S*V and U*S*V go through the fast path
+    i, j, k = tn.Index(6, "i"), tn.Index(5, "j"), tn.Index(4, "k")
+    T = tn.randomCuITensor(i, j, k, dtype=np.complex128 if cplx else np.float64, rng=rng)
+    U, S, V, spec = tn.svd(T, (i, k))
+    assert S.is_diag and not U.is_diag
+    u, v = S.inds
+    s = np.diag(S.array())
+    US = U * S
+    assert US.inds == (i, k, v) and np.allclose(US.array(), U.array() * s[None, None, :], rtol=1e-14, atol=1e-15)
+    SV = S * V
+    assert SV.inds == (u, j) and np.allclose(SV.array(), (V.array() * s[None, :]).T, rtol=1e-14, atol=1e-15)
+    a = T.array()
+    rec = tn.permute(U * S * V, T.inds).array()
+    assert np.linalg.norm(rec - a) < 1e-13 * np.linalg.norm(a)
+    # both Diag indices shared / none shared fall back to the general contraction and stay correct
+    SS = S * tn.dag(S)
+    assert abs(SS.scalar() - np.sum(s * s)) < 1e-12 * np.sum(s * s)
+    # eigen returns Diag D
+    M = tn.randomCuITensor(i, i.prime(), dtype=np.complex128 if cplx else np.float64, rng=rng)
+    Hm = M * 1.0 + tn.dag(M).replaceinds((i, i.prime()), (i.prime(), i))
+    D, Ue, _ = tn.eigen(Hm, (i,), (i.prime(),))
+    assert D.is_diag
