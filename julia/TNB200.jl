@@ -141,6 +141,18 @@ end
 # calls tnb_heff_apply; kept out of this file's executable part because ProjMPO internals differ between
 # ITensors 0.2.x patch releases -- see INTEGRATION.md for the call.
 
+# ---- Diag x Dense contraction over ONE index of the Diag tensor (src/tensor/cudiag.jl:105-161 densifies instead)
+# `shared` is the contracted label, `labelsC` the NDTensors output order with the Diag's other index already
+# substituted for `shared` (the relabel is metadata only).
+function diag_contract!(C::CuArray{ElT}, A::CuArray{ElT}, labelsA::Vector{Int32}, shared::Int32, d::CuVector,
+                        labelsC::Vector{Int32}) where {ElT}
+  check(ccall((:tnb_diag_contract, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), ndims(A), Int64[size(A)...], labelsA, ptr(A), shared, ptr(d), dtype(eltype(d)), labelsC,
+              ptr(C), stream()))
+  return C
+end
+
 # ---- TEBD gate in B form (right-canonical tensors in the Schmidt bases + Schmidt values): the unit of work of an
 # even/odd layer that can be spread over GPUs ([EXT] apply(gates, psi), examples/gate_evolution.jl:46)
 function tebd_gate_bform!(G::CuArray, lamL::CuVector{Float64}, B1::CuArray{ElT,3}, B2::CuArray{ElT,3};
