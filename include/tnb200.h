@@ -49,6 +49,9 @@ typedef enum { TNB_F64 = 0, TNB_C128 = 1 } tnb_dtype;
 /* flags for tnb_contract */
 #define TNB_CONJ_A 1
 #define TNB_CONJ_B 2
+#define TNB_HERM_UPPER 4   /* the result, matricised as (A-free modes) x (B-free modes), is Hermitian (Gram matrix):
+                              only its upper triangle is computed (tile granularity); the strictly lower part of C is
+                              left untouched.  tnb_eigh_trunc reads the upper triangle only. */
 
 /* flags for truncation (kwargs of truncate!, src/tensor/cutruncate.jl:3-7) */
 #define TNB_TRUNC_ABSOLUTE_CUTOFF 1   /* absoluteCutoff / use_absolute_cutoff */
@@ -226,7 +229,8 @@ int tnb_eigsolve_lanczos(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, c
                          int* n_matvec, void* stream);
 
 /* rho_pert <- noise * nt*nt^dagger  ([EXT] noiseterm(::ProjMPO, phi, ortho)); rho_pert is
- * (chiL*d1)^2 for ortho left, (d2*chiR)^2 for ortho right; accumulate=1 adds into it. */
+ * (chiL*d1)^2 for ortho left, (d2*chiR)^2 for ortho right; accumulate=1 adds into it.
+ * Hermitian: only the UPPER triangle is computed (what tnb_factorize_bond / tnb_eigh_trunc read). */
 int tnb_noise_term(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
                    const void* W1, const void* W2, const void* R, const void* phi, int ortho,
                    double noise, int accumulate, void* rho, void* stream);

@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_kernel(const __gr
     tn = w / gsz;
   }
   const int m0 = tm * BM, n0 = tn * BN;
-  if (p.lowerOnly && m0 + BM <= n0) return;      // tile strictly above the diagonal of a Hermitian update
+  // Hermitian result: only one triangle is needed (1: lower, rank-k update of the tridiagonalisation;
+  // 2: upper, Gram matrices feeding the 'U'-convention eigensolver) -- tiles strictly on the other side exit
+  if (p.lowerOnly == 1 && m0 + BM <= n0) return;
+  if (p.lowerOnly == 2 && n0 + BN <= m0) return;
 
   using LA = Loader<CPLX, AK, VA, BM, BK, NT, false>;
   using LB = Loader<CPLX, BKM, VB, BN, BK, NT, true>;
@@ -803,6 +806,18 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
   set_scalars(p, dtype, alpha, beta);
   p.conjA = (flags & TNB_CONJ_A) ? 1 : 0;
   p.conjB = (flags & TNB_CONJ_B) ? 1 : 0;
+  if (flags & TNB_HERM_UPPER) {
+    if (p.M != p.N) return set_err(h, TNB_ERR_BAD_ARG, "contract: TNB_HERM_UPPER needs a square (M = N) result");
+    // The kernel's (m, n) follow the OPERANDS' mode orders.  "m <= n" is C's upper triangle only if both
+    // linearisations are C's own (row offset ascending with m, column offset ascending with n, both dense):
+    // otherwise the hint is ignored and the full matrix is computed.
+    auto c_ascending = [](const Group& g, long long first) {
+      long long expect = first;
+      for (int i = 0; i < g.n; ++i) { if (g.sY[i] != expect) return false; expect *= g.ext[i]; }
+      return true;
+    };
+    if (c_ascending(p.gm, 1) && c_ascending(p.gn, (long long)p.M)) p.lowerOnly = 2;
+  }
   p.npeer = npeer;
   for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
   return launch_planned(h, dtype, p, st);

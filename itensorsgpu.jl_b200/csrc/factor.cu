@@ -211,14 +211,14 @@ static int factorize_core(Handle* h, int dtype, int64_t m, int64_t n, void* M, i
     const void* beta = rho_pert ? one : nullptr;
     if (ortho == TNB_ORTHO_LEFT) {
       // rho = M M^H (+ pert)
-      TNB_TRY(gemm_impl(h, dtype, 'N', 'C', m, m, n, nullptr, M, m, M, m, beta, rho, m, st));
+      TNB_TRY(gemm_impl(h, dtype, 'N', 'C', m, m, n, nullptr, M, m, M, m, beta, rho, m, st, 2));      // upper triangle only
       TNB_TRY(eigh_trunc_core(h, dtype, m, rho, maxdim, mindim, cutoff, 0, trunc, (double*)D, U, &nk, &err, st));
       TNB_CUDA(h, cudaMemcpyAsync(A, U, (size_t)m * nk * es, cudaMemcpyDeviceToDevice, st));
       // B = U^H M
       TNB_TRY(gemm_impl(h, dtype, 'C', 'N', nk, n, m, nullptr, U, m, M, m, nullptr, B, nk, st));
     } else {
       // rho[j,j'] = sum_i M[i,j] conj(M[i,j'])  = M^T conj(M) (+ pert)
-      TNB_TRY(gemm_impl(h, dtype, 'T', 'J', n, n, m, nullptr, M, m, M, m, beta, rho, n, st));
+      TNB_TRY(gemm_impl(h, dtype, 'T', 'J', n, n, m, nullptr, M, m, M, m, beta, rho, n, st, 2));
       TNB_TRY(eigh_trunc_core(h, dtype, n, rho, maxdim, mindim, cutoff, 0, trunc, (double*)D, U, &nk, &err, st));
       // A = M conj(U) (m x nk) ; B = U^T (nk x n)
       TNB_TRY(gemm_impl(h, dtype, 'N', 'J', m, nk, n, nullptr, M, m, U, n, nullptr, A, m, st));
@@ -439,7 +439,7 @@ int tnb_tebd_gate_bform(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, i
   if (dtype == TNB_C128) scale_rows_kernel<double2><<<g, 256, 0, ST>>>((double2*)t0, (const double2*)tt, m, n, chiL, lamL);
   else scale_rows_kernel<double><<<g, 256, 0, ST>>>((double*)t0, (const double*)tt, m, n, chiL, lamL);
   H->launches++;
-  TNB_TRY(gemm_impl(H, dtype, 'C', 'N', n, n, m, nullptr, t0, m, t0, m, nullptr, rho, n, ST));
+  TNB_TRY(gemm_impl(H, dtype, 'C', 'N', n, n, m, nullptr, t0, m, t0, m, nullptr, rho, n, ST, 2));
   int64_t nk = 0;
   double err = 0.0;
   TNB_TRY(eigh_trunc_core(H, dtype, n, rho, md, mindim, cutoff, 0, 1, (double*)D, V, &nk, &err, ST));

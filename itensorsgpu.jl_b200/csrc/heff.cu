@@ -512,7 +512,7 @@ int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
       int64_t ea[] = {d2, cr, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
       int32_t mb[] = {mS2, mR, mLpp, mS1pp, mB};
       int64_t ec[] = {cl, d1, cl, d1};     int32_t mc[] = {mLp, mS1p, mLpp, mS1pp};
-      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B, st));
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B | TNB_HERM_UPPER, st));
     }
   } else {
     {  // T1[l,s1,s2,r',c] = phi R
@@ -521,17 +521,18 @@ int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
       int64_t ec[] = {cl, d1, d2, cr, wr}; int32_t mc[] = {mL, mS1, mS2, mRp, mC};
       TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, R, 5, ec, mc, t0, nullptr, nullptr, 0, st));
     }
-    {  // nt[l,s1,r',b,s2'] = T1 W2[b,s2,s2',c]
+    {  // nt[l,s1,s2',r',b] = T1 W2[b,s2,s2',c]   ((s2',r') in rho's own order, so that the Gram below may skip
+       //                                            its strictly-lower tiles)
       int64_t ea[] = {cl, d1, d2, cr, wr}; int32_t ma[] = {mL, mS1, mS2, mRp, mC};
       int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
-      int64_t ec[] = {cl, d1, cr, wm, d2}; int32_t mc[] = {mL, mS1, mRp, mB, mS2p};
+      int64_t ec[] = {cl, d1, d2, cr, wm}; int32_t mc[] = {mL, mS1, mS2p, mRp, mB};
       TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W2, 5, ec, mc, t1, nullptr, nullptr, 0, st));
     }
     {  // rho[s2',r',s2'',r''] (+)= noise * nt conj(nt)
-      int64_t ea[] = {cl, d1, cr, wm, d2}; int32_t ma[] = {mL, mS1, mRp, mB, mS2p};
-      int32_t mb[] = {mL, mS1, mRpp, mB, mS2pp};
+      int64_t ea[] = {cl, d1, d2, cr, wm}; int32_t ma[] = {mL, mS1, mS2p, mRp, mB};
+      int32_t mb[] = {mL, mS1, mS2pp, mRpp, mB};
       int64_t ec[] = {d2, cr, d2, cr};     int32_t mc[] = {mS2p, mRp, mS2pp, mRpp};
-      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B, st));
+      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B | TNB_HERM_UPPER, st));
     }
   }
   return TNB_OK;

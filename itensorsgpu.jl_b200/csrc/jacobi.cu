@@ -422,7 +422,7 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
   const int max_sweeps = 40;
   // whole-matrix convergence test (one GEMM + one reduction): true when every pair is orthogonal to tol
   auto converged = [&](bool* yes) -> int {
-    TNB_TRY(gemm_impl(h, dtype, 'C', 'N', npad, npad, m, nullptr, Zs[cur], mz, Zs[cur], mz, nullptr, Gbig, npad, st));
+    TNB_TRY(gemm_impl(h, dtype, 'C', 'N', npad, npad, m, nullptr, Zs[cur], mz, Zs[cur], mz, nullptr, Gbig, npad, st, 2));
     TNB_CUDA(h, cudaMemsetAsync(dscal, 0, 8, st));
     gram_offmax_kernel<CPLX><<<h->num_sms * 4, 256, 0, st>>>((const T*)Gbig, npad, (const double*)danorm, (double*)dscal);
     h->launches++;
@@ -518,7 +518,7 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
     TNB_TRY(ws_alloc(h, (size_t)nn * nn * sizeof(T), &V0));
     TNB_TRY(ws_alloc(h, (size_t)mm * nn * sizeof(T), &Bm));
     TNB_TRY(ws_alloc(h, (size_t)nn * sizeof(double), &Dv));
-    TNB_TRY(gemm_impl(h, dtype, 'C', 'N', nn, nn, mm, nullptr, Awork, ld, Awork, ld, nullptr, rho, nn, st));
+    TNB_TRY(gemm_impl(h, dtype, 'C', 'N', nn, nn, mm, nullptr, Awork, ld, Awork, ld, nullptr, rho, nn, st, 2));
     const size_t mark = h->ws_off;
     TNB_TRY(eigh_dc_impl(h, dtype, nn, rho, nn, nn, (double*)Dv, V0, nn, st));
     h->ws_off = mark;

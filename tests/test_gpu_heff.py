@@ -114,4 +114,14 @@ def test_noise_term(ortho, cplx):
     L, W1, W2, R, phi = _random_bond(rng, 24, 20, 2, 5, cplx)
     got = tn.ops.noise_term(dev(L), dev(W1), dev(W2), dev(R), dev(phi), ortho, 1e-3).numpy()
     want = 1e-3 * od.noise_term(L, W1, W2, R, phi, ortho)
-    assert ot.rel_err(got, want) < 1e-12
+    # the perturbation is Hermitian and feeds the 'U'-convention eigensolver: only its upper triangle is computed
+    n = int(round(np.sqrt(want.size)))
+    g, w = np.triu(got.reshape(n, n, order="F")), np.triu(want.reshape(n, n, order="F"))
+    assert ot.rel_err(g, w) < 1e-12
+
+    # a larger case spanning several 64 x 128 tiles, through the eigen branch that consumes it
+    L, W1, W2, R, phi = _random_bond(rng, 96, 80, 2, 5, cplx)
+    got = tn.ops.noise_term(dev(L), dev(W1), dev(W2), dev(R), dev(phi), ortho, 1e-3).numpy()
+    want = 1e-3 * od.noise_term(L, W1, W2, R, phi, ortho)
+    n = int(round(np.sqrt(want.size)))
+    assert ot.rel_err(np.triu(got.reshape(n, n, order="F")), np.triu(want.reshape(n, n, order="F"))) < 1e-12
