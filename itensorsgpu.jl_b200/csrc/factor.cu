@@ -323,10 +323,8 @@ int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* d, int64_
   // survive the Lanczos and factorize arena resets -> allocate them at the very start of the arena
   // and make every later stage allocate after them (no ws_reset in between).
   const size_t lan = heff_workspace_bytes(dtype, d) + (size_t)(krylovdim + 1) * phib + (1 << 16);
-  const size_t fac = (size_t)0;
-  (void)fac;
   size_t need = phib + (noise > 0 ? al256((size_t)r * r * es) : 0);
-  size_t stage = std::max<size_t>(lan, 0);
+  size_t stage = lan;
   // factorize workspace (recomputed with the same formula as tnb_factorize_bond)
   {
     const int64_t mx = std::max(m, n);

@@ -191,11 +191,9 @@ int heff_apply_shard_impl(Handle* h, int dtype, const tnb_bond_dims* d, int64_t 
   TNB_TRY(check_dims(h, d));
   if (clp < 1 || clp > d->chiL) return set_err(h, TNB_ERR_BAD_ARG, "heff_apply_shard: bad shard extent");
   ws_reset(h);
-  tnb_bond_dims ds = *d;  // workspace scales with the shard
   const size_t base = (size_t)clp * d->chiR * d->d1 * d->d2;
   const size_t w = std::max({d->wL, d->wM, d->wR});
   const size_t half = al256(base * w * elsize(dtype));
-  (void)ds;
   TNB_TRY(ws_require(h, 2 * half));
   void *t0, *t1;
   TNB_TRY(ws_alloc(h, half, &t0));

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(1024) dc_m1_kernel(DcBufs B, const double* __r
   __shared__ double redA[32], redB[32];
   __shared__ int cnts[1024];
   __shared__ double tol_s, rho_s;
-  __shared__ int k_s, nd_s;
+  __shared__ int k_s;
   const int m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int s = B.m_s[m], n1 = B.m_n1[m], N = B.m_N[m];
   const long long n = B.n;
@@ -274,7 +274,6 @@ __global__ void __launch_bounds__(1024) dc_m1_kernel(DcBufs B, const double* __r
     }
     B.nrot[m] = nr;
     B.rho[m] = rho;
-    nd_s = nd;
     k_s = N - nd;
     B.kcnt[m] = N - nd;
     __threadfence_block();
