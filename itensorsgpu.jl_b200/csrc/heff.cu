@@ -203,7 +203,7 @@ int heff_apply_shard_impl(Handle* h, int dtype, const tnb_bond_dims* d, int64_t 
 
 // Device-side barrier over peer-mapped flag arrays: lane g publishes `epoch` into rank g's flags[rank] (system-scope
 // release) and then waits until its own flags[g] has reached `epoch` (acquire).  Runs after the GEMM in stream order,
-// so every peer store of this rank is performed before its flag.  A bounded spin (about 10 s) protects against a
+// so every peer store of this rank is performed before its flag.  A bounded spin (about 60 s) protects against a
 // rank that never arrives: the kernel then records a failure in err[0] instead of hanging the GPU.
 __global__ void peer_barrier_kernel(unsigned long long* const* flags, int rank, int world, unsigned long long epoch,
                                     double* err) {
@@ -218,7 +218,7 @@ __global__ void peer_barrier_kernel(unsigned long long* const* flags, int rank, 
   while (true) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
     if (v >= epoch) break;
-    if (clock64() - t0 > 20000000000LL) { err[0] = 1.0; break; }
+    if (clock64() - t0 > 120000000000LL) { err[0] = 1.0; break; }      // ~60 s at 1.9 GHz
     __nanosleep(200);
   }
 }
