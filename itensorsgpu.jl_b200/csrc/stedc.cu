@@ -48,6 +48,36 @@ struct DcBufs {
   const int *m_s, *m_n1, *m_N;   // merge descriptors of the current level
 };
 
+// ------------------------------------------------------------------------------------ scaling
+// The deflation tolerance 8 eps max(|d|, |z|) compares eigenvalue-scale quantities with the O(1) entries of z, so it
+// is only meaningful for |T| ~ 1 (LAPACK dstedc scales for the same reason): T is scaled to unit max-norm on
+// entry and the eigenvalues are scaled back at the end.  scal[0] = max(|d|, |e|), scal[1] = 1/scal[0] (1 if zero).
+__global__ void __launch_bounds__(1024) dc_maxnorm_kernel(const double* __restrict__ d, const double* __restrict__ e,
+                                                           long long n, double* scal) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    m = fmax(m, fabs(d[i]));
+    if (i < n - 1) m = fmax(m, fabs(e[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t = fmax(t, red[w]);
+    scal[0] = t;
+    scal[1] = (t > 0.0 && isfinite(t)) ? 1.0 / t : 1.0;
+  }
+}
+
+// x[i] *= scal[which]
+__global__ void dc_scale_kernel(double* x, long long n, const double* __restrict__ scal, int which) {
+  const double f = scal[which];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= f;
+}
+
 // ------------------------------------------------------------------------------------ leaves
 __global__ void dc_tear_kernel(double* d, const double* __restrict__ e, const int* __restrict__ splits, int nsplit) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,7 +540,7 @@ __global__ void __launch_bounds__(256) dc_order_kernel(DcBufs B) {
 // ------------------------------------------------------------------------------------ driver
 size_t stedc_ws_bytes(int64_t n) {
   size_t t = 4 * al256((size_t)n * n * sizeof(double));       // Qa, Qb, Qtmp, U
-  t += 12 * al256((size_t)n * sizeof(double)) + 8 * al256((size_t)n * sizeof(int));
+  t += 12 * al256((size_t)n * sizeof(double)) + 8 * al256((size_t)n * sizeof(int)) + 256;
   t += 2 * al256(2 * (size_t)n * sizeof(double)) + 8 * al256((size_t)(n / 16 + 64) * sizeof(int));
   return t + (1 << 16);
 }
@@ -571,6 +601,12 @@ int stedc_impl(Handle* h, int64_t n, double* d, double* e, double** Qres, double
   // gather reads the full parent row range of each child column
   TNB_CUDA(h, cudaMemsetAsync(Qa, 0, (size_t)n * n * sizeof(double), st));
   TNB_CUDA(h, cudaMemsetAsync(Qb, 0, (size_t)n * n * sizeof(double), st));
+  double* nscal;
+  TNB_TRY(dalloc(&nscal, 2));
+  dc_maxnorm_kernel<<<1, 1024, 0, st>>>(d, e, n, nscal);
+  dc_scale_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 64), 256, 0, st>>>(d, n, nscal, 1);
+  if (n > 1) dc_scale_kernel<<<(int)std::min<int64_t>((n + 254) / 256, 64), 256, 0, st>>>(e, n - 1, nscal, 1);
+  h->launches += 3;
   if (nmtot) {
     dc_tear_kernel<<<(nmtot + 127) / 128, 128, 0, st>>>(d, e, d_splits, nmtot);
     h->launches++;
@@ -615,6 +651,8 @@ int stedc_impl(Handle* h, int64_t n, double* d, double* e, double** Qres, double
     std::swap(B.dcur, B.dout);
     std::swap(B.idx, B.idxo);
   }
+  dc_scale_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 64), 256, 0, st>>>(B.dcur, n, nscal, 0);      // eigenvalues back to T's scale
+  h->launches++;
   *Qres = Qin; *dres = B.dcur; *idxres = B.idx;
   return check_cuda(h, cudaGetLastError(), "stedc");
 }

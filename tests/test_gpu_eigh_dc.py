@@ -72,7 +72,7 @@ def _stedc(d, e):
     return lam.cpu().numpy(), Z.cpu().numpy().reshape((n, n), order="F")
 
 
-@pytest.mark.parametrize("kind", ["random", "wilkinson", "graded", "constant", "decoupled"])
+@pytest.mark.parametrize("kind", ["random", "wilkinson", "graded", "constant", "decoupled", "tiny1e-100", "small1e-8", "huge1e100", "zero"])
 @pytest.mark.parametrize("n", [1, 2, 40, 64, 65, 129, 300, 1000])
 def test_stedc(kind, n):
     rng = np.random.default_rng(7 * n + len(kind))
@@ -85,13 +85,19 @@ def test_stedc(kind, n):
         e = 0.3 * np.sqrt(d[:-1] * d[1:]) if n > 1 else np.zeros(0)
     elif kind == "constant":
         d, e = np.full(n, 2.0), np.full(max(n - 1, 0), -1.0)
+    elif kind in ("tiny1e-100", "small1e-8", "huge1e100"):
+        # the deflation tolerance is defined for a unit-norm matrix: the solver must scale (LAPACK dstedc does)
+        sc = {"tiny1e-100": 1e-100, "small1e-8": 1e-8, "huge1e100": 1e100}[kind]
+        d, e = sc * rng.standard_normal(n), sc * rng.standard_normal(max(n - 1, 0))
+    elif kind == "zero":
+        d, e = np.zeros(n), np.zeros(max(n - 1, 0))
     else:
         d, e = rng.standard_normal(n), rng.standard_normal(max(n - 1, 0))
         e[::7] = 0.0
     lam, Z = _stedc(d, e)
     T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
     w = np.linalg.eigvalsh(T)[::-1]
-    nrm = max(np.max(np.abs(w)), 1e-300)
+    nrm = max(np.max(np.abs(w)), 1e-300) if w.size else 1.0
     assert np.max(np.abs(lam - w)) < 2e-14 * nrm * max(1, n / 100)
     assert np.linalg.norm(Z.T @ Z - np.eye(n)) < 2e-13 * max(1, n / 100)
     assert np.linalg.norm(T @ Z - Z * lam[None, :]) < 2e-13 * nrm * max(1, n / 100)
@@ -134,3 +140,20 @@ def test_eigh_dc_density_matrix_truncated(cplx):
     # the kept subspace agrees with LAPACK's: projectors equal up to the gap-limited accuracy
     P1, P2 = U @ U.conj().T, Ur @ Ur.conj().T
     assert np.linalg.norm(rho @ P1 - rho @ P2) < 1e-12 * Dr[0]
+
+
+@pytest.mark.parametrize("scale", [1e-90, 1e-7, 1e60])
+def test_eigh_and_svd_are_scale_invariant(scale):
+    """eigen / svd of s*A must be s * (eigen / svd of A): nothing on the path may assume a unit-norm input."""
+    from itensorsgpu_b200 import tn
+    rng = np.random.default_rng(9)
+    n = 300
+    A = _herm(rng, n, False)
+    D, U, _ = tn.ops.eigh(dev(scale * A))
+    w = np.linalg.eigvalsh(A)[::-1]
+    assert np.max(np.abs(D.cpu().numpy() / scale - w)) < 1e-12 * np.max(np.abs(w))
+    Un = U.numpy()
+    assert np.linalg.norm(Un.T @ Un - np.eye(n)) < 1e-11
+    B = rand(rng, (320, 300), False)
+    Us, S, Vs, _ = tn.ops.svd(dev(np.sqrt(scale) * B))
+    assert np.max(np.abs(S.cpu().numpy() / np.sqrt(scale) - np.linalg.svd(B, compute_uv=False))) < 1e-12 * np.linalg.norm(B, 2)

@@ -244,6 +244,17 @@ def merge(d1, Q1, d2, Q2, rho_e):
 
 
 def stedc(d, e, leaf=32, stats=None):
+    """Scale to unit max-norm first (as LAPACK dstedc does): the deflation tolerance 8 eps max(|d|, |z|) compares
+    eigenvalue-scale quantities with the O(1) entries of z and is only meaningful for |T| ~ 1."""
+    d = np.asarray(d, float); e = np.asarray(e, float)
+    s = max(np.max(np.abs(d), initial=0.0), np.max(np.abs(e), initial=0.0))
+    if s == 0.0:
+        return d.copy(), np.eye(len(d))
+    w, Q = _stedc_unit(d / s, e / s, leaf, stats)
+    return w * s, Q
+
+
+def _stedc_unit(d, e, leaf=32, stats=None):
     n = len(d)
     if n <= leaf:
         T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
@@ -253,8 +264,8 @@ def stedc(d, e, leaf=32, stats=None):
     r = e[n1 - 1]
     d1 = d[:n1].copy(); d2 = d[n1:].copy()
     d1[-1] -= abs(r); d2[0] -= abs(r)
-    w1, Q1 = stedc(d1, e[:n1 - 1], leaf, stats)
-    w2, Q2 = stedc(d2, e[n1:], leaf, stats)
+    w1, Q1 = _stedc_unit(d1, e[:n1 - 1], leaf, stats)
+    w2, Q2 = _stedc_unit(d2, e[n1:], leaf, stats)
     w, Q, st = merge(w1, Q1, w2, Q2, r)
     if stats is not None:
         stats.append(st)
