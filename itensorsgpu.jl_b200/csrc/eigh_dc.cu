@@ -21,12 +21,56 @@ int stedc_impl(Handle* h, int64_t n, double* d, double* e, double** Qres, double
 int backtransform_impl(Handle* h, int dtype, int64_t n, const void* Vst, const void* tau, void* X, int64_t ldx, int64_t kx,
                        cudaStream_t st);
 
+// ---- range guard (what LAPACK's drivers do with lascl): squares of entries below 1e-154 underflow in the Householder
+// norms, so inputs whose largest entry lies outside [1e-100, 1e100] are scaled to unit max-norm and the
+// eigenvalues / singular values scaled back.  All on the device: scal[0] = max|a_ij| (upper triangle),
+// scal[1] = factor applied to the input (1 in the normal range), scal[2] = 1 / scal[1].
 template <typename T>
-__global__ void herm_from_upper_kernel(T* A, long long n) {
+__global__ void __launch_bounds__(256) absmax_kernel(const T* __restrict__ A, long long rows, long long cols, long long ld,
+                                                      int upper_only, double* scal) {
+  double m = 0.0;
+  for (long long eidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; eidx < rows * cols; eidx += (long long)gridDim.x * blockDim.x) {
+    const long long i = eidx % rows, j = eidx / rows;
+    if (upper_only && i > j) continue;
+    const T v = A[i + j * ld];
+    m = fmax(m, fmax(fabs(a_re(v)), fabs(a_im(v))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0 && isfinite(m))
+    atomicMax((unsigned long long*)scal, (unsigned long long)__double_as_longlong(m));     // order-preserving for doubles >= 0
+}
+
+__global__ void range_factor_kernel(double* scal) {
+  const double m = scal[0];
+  const double f = (m > 0.0 && (m < 1e-100 || m > 1e100)) ? 1.0 / m : 1.0;
+  scal[1] = f;
+  scal[2] = 1.0 / f;
+}
+
+__global__ void scale_vec_kernel(double* x, long long n, const double* __restrict__ scal, int which) {
+  const double f = scal[which];
+  if (f == 1.0) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= f;
+}
+
+template <typename T>
+__global__ void herm_from_upper_kernel(T* A, long long n, const double* __restrict__ scal) {
+  const double f = scal[1];
   for (long long eidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; eidx < n * n; eidx += (long long)gridDim.x * blockDim.x) {
     const long long i = eidx % n, j = eidx / n;
-    if (i > j) A[eidx] = a_conj(A[j + i * n]);
-    else if (i == j) A[eidx] = a_real<T>(a_re(A[eidx]));
+    if (i > j) A[eidx] = a_scale(a_conj(A[j + i * n]), f);
+  }
+}
+
+// second pass (the lower triangle above read the UNSCALED upper one): scale the upper triangle, make the diagonal real
+template <typename T>
+__global__ void herm_scale_upper_kernel(T* A, long long n, const double* __restrict__ scal) {
+  const double f = scal[1];
+  for (long long eidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; eidx < n * n; eidx += (long long)gridDim.x * blockDim.x) {
+    const long long i = eidx % n, j = eidx / n;
+    if (i < j) { if (f != 1.0) A[eidx] = a_scale(A[eidx], f); }
+    else if (i == j) A[eidx] = a_real<T>(a_re(A[eidx]) * f);
   }
 }
 
@@ -47,7 +91,7 @@ __global__ void __launch_bounds__(256) pick_desc_kernel(const double* __restrict
 size_t eigh_dc_ws_bytes(int dtype, int64_t n, int64_t kmax) {
   const size_t es = elsize(dtype);
   size_t stage = std::max(tridiag_ws_bytes(dtype, n), stedc_ws_bytes(n) + backtransform_ws_bytes(dtype, n, kmax));
-  return 2 * al256((size_t)n * sizeof(double)) + al256((size_t)n * es) + stage + 8192;
+  return 2 * al256((size_t)n * sizeof(double)) + al256((size_t)n * es) + 256 + stage + 8192;
 }
 
 template <bool CPLX>
@@ -58,8 +102,14 @@ static int eigh_dc_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks,
   TNB_TRY(ws_alloc(h, (size_t)n * sizeof(double), &dv));
   TNB_TRY(ws_alloc(h, (size_t)n * sizeof(double), &ev));
   TNB_TRY(ws_alloc(h, (size_t)n * sizeof(T), &tau));
-  herm_from_upper_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)A, n);
-  h->launches++;
+  void* rscal;
+  TNB_TRY(ws_alloc(h, 64, &rscal));
+  TNB_CUDA(h, cudaMemsetAsync(rscal, 0, 64, st));
+  absmax_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((const T*)A, n, n, n, 1, (double*)rscal);
+  range_factor_kernel<<<1, 1, 0, st>>>((double*)rscal);
+  herm_from_upper_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)A, n, (const double*)rscal);
+  herm_scale_upper_kernel<T><<<h->num_sms * 4, 256, 0, st>>>((T*)A, n, (const double*)rscal);
+  h->launches += 4;
   const size_t mark = h->ws_off;
   TNB_TRY(tridiag_impl(h, dtype, n, A, (double*)dv, (double*)ev, tau, st));
   h->ws_off = mark;     // release the panel buffers (stream order keeps them valid until the kernels ran)
@@ -69,7 +119,8 @@ static int eigh_dc_core(Handle* h, int64_t n, void* A, int64_t kmax, int64_t ks,
   const long long cols = std::max<int64_t>(kmax, ks);
   dim3 g((unsigned)std::min<int64_t>((n + 255) / 256, 16), (unsigned)cols);
   pick_desc_kernel<T><<<g, 256, 0, st>>>(Q, n, lam, idx, D, ks, (T*)U, ldu, kmax);
-  h->launches++;
+  scale_vec_kernel<<<(int)std::min<int64_t>((ks + 255) / 256, 64), 256, 0, st>>>(D, ks, (const double*)rscal, 2);
+  h->launches += 2;
   TNB_TRY(backtransform_impl(h, dtype, n, A, tau, U, ldu, kmax, st));
   return check_cuda(h, cudaGetLastError(), "eigh_dc");
 }

@@ -484,6 +484,34 @@ static int sort_desc(Handle* h, const double* keys_dev, int npad, int* perm_dev,
   return TNB_OK;
 }
 
+// range guard of svd (see eigh_dc.cu): largest |entry| and a scaled copy for inputs outside [1e-100, 1e100]
+template <bool CPLX>
+__global__ void __launch_bounds__(256) svd_absmax_kernel(const typename JT<CPLX>::T* __restrict__ A, long long rows, long long cols,
+                                                          long long ld, double* out) {
+  double m = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (long long)gridDim.x * blockDim.x) {
+    const auto v = A[(e % rows) + (e / rows) * ld];
+    if constexpr (CPLX) m = fmax(m, fmax(fabs(v.x), fabs(v.y))); else m = fmax(m, fabs(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0 && isfinite(m)) atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(m));
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) svd_scaled_copy_kernel(typename JT<CPLX>::T* out, const typename JT<CPLX>::T* __restrict__ A,
+                                                               long long rows, long long cols, long long ld, double f) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += (long long)gridDim.x * blockDim.x) {
+    auto v = A[(e % rows) + (e / rows) * ld];
+    if constexpr (CPLX) { v.x *= f; v.y *= f; } else v *= f;
+    out[e] = v;
+  }
+}
+
+__global__ void svd_scale_s_kernel(double* S, long long n, double f) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) S[i] *= f;
+}
+
 // Thin SVD of A (m x n): U (m x kmax), S (kmax), V (n x kmax) with A ~ U diag(S) V^T.
 // Works on the taller orientation internally.  Arena must have been sized by the caller
 // (svd_ws_bytes).  If P_out != null it receives S^2 (kmax entries, device).
@@ -492,6 +520,26 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
                     int64_t ldu, double* S, void* V, int64_t ldv, cudaStream_t st) {
   using T = typename JT<CPLX>::T;
   const int dtype = CPLX ? TNB_C128 : TNB_F64;
+  // range guard: squares of entries underflow / overflow in the Gram matrices outside ~[1e-154, 1e154]
+  double unscale = 1.0;
+  {
+    void* dmax;
+    TNB_TRY(ws_alloc(h, 64, &dmax));
+    TNB_CUDA(h, cudaMemsetAsync(dmax, 0, 8, st));
+    svd_absmax_kernel<CPLX><<<h->num_sms * 4, 256, 0, st>>>((const T*)A, m, n, lda, (double*)dmax);
+    h->launches++;
+    TNB_CUDA(h, cudaMemcpyAsync(h->scal_host + 102, dmax, 8, cudaMemcpyDeviceToHost, st));
+    TNB_CUDA(h, cudaStreamSynchronize(st));
+    const double amax = h->scal_host[102];
+    if (amax > 0.0 && (amax < 1e-100 || amax > 1e100)) {
+      void* As;
+      TNB_TRY(ws_alloc(h, (size_t)m * n * sizeof(T), &As));
+      svd_scaled_copy_kernel<CPLX><<<h->num_sms * 4, 256, 0, st>>>((T*)As, (const T*)A, m, n, lda, 1.0 / amax);
+      h->launches++;
+      A = As; lda = m;
+      unscale = amax;
+    }
+  }
   const bool transposed = m < n;
   const void* Awork = A;
   int64_t mm = m, nn = n, ld = lda;
@@ -537,6 +585,10 @@ static int svd_core(Handle* h, int64_t m, int64_t n, const void* A, int64_t lda,
   std::vector<int> pv;
   TNB_TRY(sort_desc(h, (const double*)nrm, jo.npad, (int*)perm, (double*)sorted, keys, pv, st));
   TNB_CUDA(h, cudaMemcpyAsync(S, sorted, ks * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (unscale != 1.0) {
+    svd_scale_s_kernel<<<(int)std::min<int64_t>((ks + 255) / 256, 64), 256, 0, st>>>(S, ks, unscale);
+    h->launches++;
+  }
   // left factor of the worked matrix = normalised G columns; right factor = V columns.
   // Worked matrix = Uw S Vw^H with Uw = normalised G columns, Vw = accumulated rotations; the
   // output convention is A = U S Vout^T.  Not transposed: U = Uw, Vout = conj(Vw).
@@ -560,7 +612,7 @@ size_t svd_ws_bytes(int dtype, int64_t m, int64_t n) {
   jacobi_geometry(dtype, nn, &nblk, &npad);
   const size_t es = elsize(dtype);
   const size_t pre = 2 * al256((size_t)nn * nn * es) + al256((size_t)mm * nn * es) + al256(nn * 8) + eigh_dc_ws_bytes(dtype, nn, nn);
-  return jacobi_ws_bytes(dtype, mm, nn, true) + al256((size_t)m * n * es) + 3 * al256(npad * 8) + pre + 4096;
+  return jacobi_ws_bytes(dtype, mm, nn, true) + 2 * al256((size_t)m * n * es) + 3 * al256(npad * 8) + pre + 4096 + 256;
 }
 
 int svd_impl(Handle* h, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, int64_t kmax, int64_t ks, void* U,

@@ -142,9 +142,10 @@ def test_eigh_dc_density_matrix_truncated(cplx):
     assert np.linalg.norm(rho @ P1 - rho @ P2) < 1e-12 * Dr[0]
 
 
-@pytest.mark.parametrize("scale", [1e-90, 1e-7, 1e60])
+@pytest.mark.parametrize("scale", [1e-240, 1e-90, 1e-7, 1e60, 1e240])
 def test_eigh_and_svd_are_scale_invariant(scale):
-    """eigen / svd of s*A must be s * (eigen / svd of A): nothing on the path may assume a unit-norm input."""
+    """eigen / svd of s*A must be s * (eigen / svd of A): nothing on the path may assume a unit-norm input
+    (1e+-240: entries whose squares leave the double range -- the drivers rescale, like LAPACK's lascl)."""
     from itensorsgpu_b200 import tn
     rng = np.random.default_rng(9)
     n = 300
