@@ -204,6 +204,61 @@ int tnb_peer_close(tnb_handle_t h, void* ptr);
 int tnb_peer_free(tnb_handle_t h, void* ptr);
 int tnb_peer_status(tnb_handle_t h, void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU peer group -- */
+/* One process per GPU on one NVSwitch node.  tnb_comm_init registers this rank's peer group on the handle: rank,
+ * world (<= 8) and `world` peer-mapped flag arrays (>= 8 uint64 each, zero-initialised; own one included; from
+ * tnb_peer_alloc / tnb_peer_open).  The library then numbers its own barrier epochs, so every rank must issue the
+ * same sequence of collective calls (the *_shard entry points below, tnb_comm_barrier, tnb_comm_allgather).  There
+ * is no library collective on the data path: results cross NVLink as peer stores from GEMM epilogues or as
+ * copy-engine writes into peer-mapped buffers.  (The reference's only multi-GPU attempt is dead cuBLASMg code,
+ * src/tensor/dense.jl:195-265.) */
+int tnb_comm_init(tnb_handle_t h, int rank, int world, void* const* flag_peers);
+int tnb_comm_finalize(tnb_handle_t h);
+/* Device-side barrier over the group, stream-ordered and asynchronous. */
+int tnb_comm_barrier(tnb_handle_t h, void* stream);
+/* All-gather over peer memory: barrier; bytes [offset + rank*bytes_per_rank, + bytes_per_rank) of this rank's own
+ * buffer bufs[rank] are copied to the same place in every peer buffer bufs[g]; barrier.  Asynchronous. */
+int tnb_comm_allgather(tnb_handle_t h, void* const* bufs, size_t offset_bytes, size_t bytes_per_rank, void* stream);
+/* Bytes each rank's staging buffer must hold for the sharded environment updates / noise term at bond dimension
+ * <= chi, site dimension d, MPO bond <= w. */
+size_t tnb_shard_stage_bytes(int dtype, int64_t chi, int32_t d, int32_t w, int world);
+
+/* Sharded [EXT] makeL!: rank g holds L_slab[l, l'_g, a] (chiL/world columns of l') and produces
+ * Lnew_slab[r, r'_g, b] (chiR/world columns of r').  Two GEMMs with 1/world of the flops each and one all-gather of
+ * the small-K intermediate through the peer-mapped staging buffers stage_peers[g]. */
+int tnb_env_update_left_shard(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d, int32_t wL, int32_t wR,
+                              const void* L_slab, const void* A, const void* W, void* const* stage_peers,
+                              void* Lnew_slab, void* stream);
+/* Sharded [EXT] makeR!: R and Rnew are replicated (full) on every rank; the flops are split 1/world and the slabs
+ * of the result are all-gathered through the staging buffers. */
+int tnb_env_update_right_shard(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiR, int32_t d, int32_t wL, int32_t wR,
+                               const void* R, const void* A, const void* W, void* const* stage_peers, void* Rnew,
+                               void* stream);
+/* tnb_eigsolve_lanczos with the matvec sharded over the output bond: every H*v is tnb_heff_apply_shard_fused into
+ * the alternating peer-mapped full-vector buffers out_a_peers / out_b_peers ([chiL,d1,d2,chiR] each, one per rank);
+ * Krylov vectors and all vector operations are replicated, so no scalar ever crosses GPUs. */
+int tnb_eigsolve_lanczos_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L_slab, const void* W1,
+                               const void* W2, const void* R, void* phi, void* const* out_a_peers,
+                               void* const* out_b_peers, int krylovdim, int maxiter, double tol, double* energy,
+                               int* n_matvec, void* stream);
+/* tnb_dmrg_bond_step on a peer group: phi = A1*A2 (replicated), sharded Lanczos, noise term with its two large
+ * contractions sharded (stage_peers; may be NULL when noise == 0), truncated factorization replicated (same
+ * deterministic kernels on identical inputs on every rank -> bit-identical A1, A2, n_keep; nothing is broadcast).
+ * Buffer sizes as for tnb_dmrg_bond_step. */
+int tnb_dmrg_bond_step_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int64_t chiM, const void* L_slab,
+                             const void* W1, const void* W2, const void* R, void* A1, void* A2, int ortho,
+                             int which_decomp, int64_t maxdim, int64_t mindim, double cutoff, double noise,
+                             int krylovdim, int maxiter, void* const* out_a_peers, void* const* out_b_peers,
+                             void* const* stage_peers, double* energy, int64_t* n_keep, double* truncerr,
+                             void* stream);
+/* End-to-end sharded matvec with HOST buffers (bench.py `e2e` at N > 1): this rank uploads only its r-chunk of
+ * phi_host (1/world of the vector; chunk g = r in [g*ceil(chiR/world), ...)), forwards it to the peer-mapped phi
+ * buffers of all ranks over NVLink, runs its slab with the all-gather fused into step 4, and downloads only its l'
+ * slab of H*phi into out_host (strided window; phi_host / out_host have phi's layout).  Synchronous. */
+int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L_slab, const void* W1,
+                              const void* W2, const void* R, const void* phi_host, void* const* phi_peers,
+                              void* const* out_peers, void* out_host, void* stream);
+
 /* Same, phi and out in HOST memory (pinned or pageable): H2D + apply + D2H, synchronous.
  * This is the end-to-end form timed by bench.py `e2e`. */
 int tnb_heff_apply_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L,
@@ -237,7 +292,12 @@ int tnb_noise_term(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const v
 
 /* Split phi[l,s1,s2,r] -> A[l,s1,k] * B[k,s2,r] with truncation, orthogonality side and
  * normalisation ([EXT] replacebond! -> factorize; svd/eigen bodies at
- * src/tensor/culinearalgebra.jl:33-108).  A, B sized for kmax = min(chiL*d1, d2*chiR, maxdim).
+ * src/tensor/culinearalgebra.jl:33-108).  Output capacity: A holds chiL*d1*kmax elements and B kmax*d2*chiR with
+ *   kmax = min(r, maxdim),  r = min(chiL*d1, d2*chiR) on the svd / qr branches,
+ *                           r = chiL*d1 (ortho left) or d2*chiR (ortho right) on the EIGEN branch
+ * (which_decomp = EIGEN, or AUTO with rho_pert != NULL or cutoff > 1e-12): a perturbed density matrix can have
+ * more non-zero eigenvalues than min(m, n), and like [EXT] factorize_eigen the call keeps up to maxdim of them.
+ * maxdim <= 0 means "no limit" (kmax = r).  Matrix sizes up to 32768 (eigensolver workspace 4 n^2 doubles).
  * rho_pert may be NULL.  Synchronises. */
 int tnb_factorize_bond(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, void* phi,
                        int ortho, int which_decomp, int64_t maxdim, int64_t mindim,
@@ -246,8 +306,9 @@ int tnb_factorize_bond(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, voi
 
 /* One full two-site DMRG bond update: phi = A1*A2; Lanczos; optional noise; factorize.
  * In: A1[chiL,d1,chiM], A2[chiM,d2,chiR].  Out (overwritten): A1[chiL,d1,k], A2[k,d2,chiR] with
- * k = *n_keep; both buffers must hold max(input, chiL*d1*kmax / kmax*d2*chiR) elements,
- * kmax = min(chiL*d1, d2*chiR, maxdim). */
+ * k = *n_keep; both buffers must hold max(input, chiL*d1*kmax / kmax*d2*chiR) elements, kmax as documented at
+ * tnb_factorize_bond (the eigen branch -- noise > 0 or cutoff > 1e-12 -- is bounded by the ORTHO side's dimension,
+ * not by min(m, n)). */
 int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int64_t chiM, const void* L,
                        const void* W1, const void* W2, const void* R, void* A1, void* A2,
                        int ortho, int which_decomp, int64_t maxdim, int64_t mindim,
@@ -255,7 +316,8 @@ int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int
                        double* energy, int64_t* n_keep, double* truncerr, void* stream);
 
 /* theta[l,s1',s2',r] <- sum G[s1',s2',s1,s2] A1[l,s1,k] A2[k,s2,r]  then left-orthogonal
- * split with truncation ([EXT] apply / product(o, psi); examples/gate_evolution.jl:46). */
+ * split with truncation ([EXT] apply / product(o, psi); examples/gate_evolution.jl:46).  A1 / A2 capacities as for
+ * tnb_dmrg_bond_step with ortho left (cutoff > 1e-12 selects the eigen branch: kmax = min(chiL*d1, maxdim)). */
 int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR,
                         int32_t d1, int32_t d2, const void* G, void* A1, void* A2,
                         int64_t maxdim, int64_t mindim, double cutoff, int64_t* n_keep,

@@ -68,6 +68,19 @@ SIGNATURES = {
     "tnb_peer_close": (_int, [_vp, _vp]),
     "tnb_peer_free": (_int, [_vp, _vp]),
     "tnb_peer_status": (_int, [_vp, _vp]),
+    "tnb_comm_init": (_int, [_vp, _int, _int, C.POINTER(_vp)]),
+    "tnb_comm_finalize": (_int, [_vp]),
+    "tnb_comm_barrier": (_int, [_vp, _vp]),
+    "tnb_comm_allgather": (_int, [_vp, C.POINTER(_vp), C.c_size_t, C.c_size_t, _vp]),
+    "tnb_shard_stage_bytes": (C.c_size_t, [_int, _i64, _i32, _i32, _int]),
+    "tnb_env_update_left_shard": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_vp), _vp, _vp]),
+    "tnb_env_update_right_shard": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_vp), _vp, _vp]),
+    "tnb_eigsolve_lanczos_shard": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _int,
+                                          _int, _dbl, _pdbl, _pint, _vp]),
+    "tnb_dmrg_bond_step_shard": (_int, [_vp, _int, _pbd, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _i64, _dbl,
+                                        _dbl, _int, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _pdbl, _pi64,
+                                        _pdbl, _vp]),
+    "tnb_heff_apply_shard_host": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp]),
     "tnb_heff_apply_host": (_int, [_vp, _int, _pbd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnb_env_update_left": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tnb_env_update_right": (_int, [_vp, _int, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -256,6 +256,13 @@ static int factorize_core(Handle* h, int dtype, int64_t m, int64_t n, void* M, i
   return TNB_OK;
 }
 
+int factorize_core_pub(Handle* h, int dtype, int64_t m, int64_t n, void* M, int ortho, int which, int64_t maxdim,
+                       int64_t mindim, double cutoff, const void* rho_pert, int normalize, void* A, void* B,
+                       int64_t* n_keep, double* truncerr, cudaStream_t st) {
+  return factorize_core(h, dtype, m, n, M, ortho, which, maxdim, mindim, cutoff, rho_pert, normalize, A, B, n_keep, truncerr, st);
+}
+size_t factorize_ws_bytes_pub(int dtype, int64_t m, int64_t n) { return factorize_ws_bytes(dtype, m, n); }
+
 }  // namespace tnb
 
 using namespace tnb;

@@ -202,17 +202,18 @@ int heff_apply_shard_impl(Handle* h, int dtype, const tnb_bond_dims* d, int64_t 
 }
 
 // Device-side barrier over peer-mapped flag arrays: lane g publishes `epoch` into rank g's flags[rank] (system-scope
-// release) and then waits until its own flags[g] has reached `epoch` (acquire).  Runs after the GEMM in stream order,
-// so every peer store of this rank is performed before its flag.  A bounded spin (about 60 s) protects against a
-// rank that never arrives: the kernel then records a failure in err[0] instead of hanging the GPU.
-__global__ void peer_barrier_kernel(unsigned long long* const* flags, int rank, int world, unsigned long long epoch,
-                                    double* err) {
+// release) and then waits until its own flags[g] has reached `epoch` (acquire).  Runs after the preceding work in
+// stream order, so every peer store of this rank is performed before its flag.  A bounded spin (about 60 s)
+// protects against a rank that never arrives: the kernel then records a failure in err[0] instead of hanging the GPU.
+struct FlagPtrs { unsigned long long* p[TNB_MAX_PEERS]; };
+
+__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, unsigned long long epoch, double* err) {
   const int g = threadIdx.x;
   if (g >= world) return;
   __threadfence_system();
-  unsigned long long* remote = flags[g] + rank;
+  unsigned long long* remote = flags.p[g] + rank;
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
-  const unsigned long long* mine = flags[rank] + g;
+  const unsigned long long* mine = flags.p[rank] + g;
   const long long t0 = clock64();
   unsigned long long v = 0;
   while (true) {
@@ -223,6 +224,49 @@ __global__ void peer_barrier_kernel(unsigned long long* const* flags, int rank, 
   }
 }
 
+static int peer_barrier(Handle* h, void* const* flag_peers, int rank, int world, unsigned long long epoch, cudaStream_t st) {
+  FlagPtrs fp;
+  for (int g = 0; g < TNB_MAX_PEERS; ++g) fp.p[g] = g < world ? (unsigned long long*)flag_peers[g] : nullptr;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, epoch, h->scal + 200);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "peer barrier");
+}
+
+int comm_barrier(Handle* h, cudaStream_t st) {
+  if (!h->comm.on) return set_err(h, TNB_ERR_BAD_ARG, "no peer group on this handle (tnb_comm_init)");
+  if (h->comm.world == 1) return TNB_OK;
+  h->comm.epoch++;
+  return peer_barrier(h, (void* const*)h->comm.flags, h->comm.rank, h->comm.world, h->comm.epoch, st);
+}
+
+int comm_allgather(Handle* h, void* const* bufs, size_t off, size_t bytes, cudaStream_t st) {
+  if (!h->comm.on) return set_err(h, TNB_ERR_BAD_ARG, "no peer group on this handle (tnb_comm_init)");
+  const int rank = h->comm.rank, world = h->comm.world;
+  if (world == 1) return TNB_OK;
+  TNB_TRY(comm_barrier(h, st));      // every rank is done with the previous contents of the peer buffers
+  const char* src = (const char*)bufs[rank] + off + (size_t)rank * bytes;
+  for (int i = 1; i < world; ++i) {  // staggered destinations: no two ranks target the same peer at once
+    const int g = (rank + i) % world;
+    TNB_CUDA(h, cudaMemcpyAsync((char*)bufs[g] + off + (size_t)rank * bytes, src, bytes, cudaMemcpyDefault, st));
+  }
+  return comm_barrier(h, st);        // all slabs have landed everywhere
+}
+
+size_t heff_shard_ws_bytes(int dtype, const tnb_bond_dims* d, int64_t clp) {
+  const size_t base = (size_t)clp * d->chiR * d->d1 * d->d2;
+  const size_t w = std::max({d->wL, d->wM, d->wR});
+  return 2 * al256(base * w * elsize(dtype));
+}
+
+int heff_shard_fused_core(Handle* h, int dtype, const tnb_bond_dims* d, int rank, int world, int64_t clp,
+                          const void* Lslab, const void* W1, const void* W2, const void* R, const void* phi,
+                          void* const* out_peers, void* t0, void* t1, cudaStream_t st) {
+  PeerOut po;
+  po.npeer = world;
+  for (int g = 0; g < world; ++g) po.base[g] = (char*)out_peers[g] + (size_t)rank * clp * elsize(dtype);
+  return heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, nullptr, t0, t1, st, &po);
+}
+
 int heff_apply_shard_fused_impl(Handle* h, int dtype, const tnb_bond_dims* d, int rank, int world, int64_t clp,
                                 const void* Lslab, const void* W1, const void* W2, const void* R, const void* phi,
                                 void* const* out_peers, void* const* flag_peers, unsigned long long epoch, cudaStream_t st) {
@@ -230,23 +274,13 @@ int heff_apply_shard_fused_impl(Handle* h, int dtype, const tnb_bond_dims* d, in
   if (world < 1 || world > TNB_MAX_PEERS || rank < 0 || rank >= world) return set_err(h, TNB_ERR_BAD_ARG, "heff_apply_shard_fused: rank/world");
   if (clp < 1 || clp * world != d->chiL) return set_err(h, TNB_ERR_BAD_ARG, "heff_apply_shard_fused: chiL must be world * lp_extent");
   ws_reset(h);
-  const size_t base = (size_t)clp * d->chiR * d->d1 * d->d2;
-  const size_t w = std::max({d->wL, d->wM, d->wR});
-  const size_t half = al256(base * w * elsize(dtype));
-  TNB_TRY(ws_require(h, 2 * half + 4096));
-  void *t0, *t1, *fp;
-  TNB_TRY(ws_alloc(h, half, &t0));
-  TNB_TRY(ws_alloc(h, half, &t1));
-  TNB_TRY(ws_alloc(h, TNB_MAX_PEERS * sizeof(void*), &fp));
-  PeerOut po;
-  po.npeer = world;
-  // base[0] must be this rank's own buffer only for bookkeeping; order is irrelevant to the stores
-  for (int g = 0; g < world; ++g) po.base[g] = (char*)out_peers[g] + (size_t)rank * clp * elsize(dtype);
-  TNB_TRY(heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, nullptr, t0, t1, st, &po));
-  TNB_CUDA(h, cudaMemcpyAsync(fp, flag_peers, world * sizeof(void*), cudaMemcpyHostToDevice, st));
-  peer_barrier_kernel<<<1, 32, 0, st>>>((unsigned long long* const*)fp, rank, world, epoch, h->scal + 200);
-  h->launches++;
-  return check_cuda(h, cudaGetLastError(), "peer barrier");
+  const size_t hw = heff_shard_ws_bytes(dtype, d, clp);
+  TNB_TRY(ws_require(h, hw));
+  void *t0, *t1;
+  TNB_TRY(ws_alloc(h, hw / 2, &t0));
+  TNB_TRY(ws_alloc(h, hw / 2, &t1));
+  TNB_TRY(heff_shard_fused_core(h, dtype, d, rank, world, clp, Lslab, W1, W2, R, phi, out_peers, t0, t1, st));
+  return peer_barrier(h, flag_peers, rank, world, epoch, st);
 }
 
 // ------------------------------------------------------------------------------------
@@ -413,7 +447,7 @@ static int vec_grid(Handle* h, long long n2) {
 
 int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
                  const void* W2, const void* R, void* phi, int krylovdim, int maxiter, double tol,
-                 double* energy, int* n_matvec, cudaStream_t st) {
+                 double* energy, int* n_matvec, cudaStream_t st, const ShardCtx* sc) {
   TNB_TRY(check_dims(h, d));
   if (krylovdim < 1 || krylovdim > KRYLOV_MAX) return set_err(h, TNB_ERR_BAD_ARG, "lanczos: krylovdim must be in 1..%d", KRYLOV_MAX);
   if (maxiter < 1) return set_err(h, TNB_ERR_BAD_ARG, "lanczos: maxiter < 1");
@@ -425,13 +459,15 @@ int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, co
   const int tail = (int)(nd & 1);
   const size_t vbytes = al256((size_t)n * es);
   ws_reset(h);
-  const size_t hw = heff_ws_bytes(dtype, d);
+  const size_t hw = sc ? heff_shard_ws_bytes(dtype, d, sc->clp) : heff_ws_bytes(dtype, d);
   TNB_TRY(ws_require(h, hw + (size_t)(krylovdim + 1) * vbytes + 1024));
-  void *t0, *t1, *Vb, *w;
+  void *t0, *t1, *Vb, *w = nullptr;
   TNB_TRY(ws_alloc(h, hw / 2, &t0));
   TNB_TRY(ws_alloc(h, hw / 2, &t1));
   TNB_TRY(ws_alloc(h, (size_t)krylovdim * vbytes, &Vb));
-  TNB_TRY(ws_alloc(h, vbytes, &w));
+  if (!sc) TNB_TRY(ws_alloc(h, vbytes, &w));
+  // sharded matvec: every rank must have finished with the peer-visible result buffers of earlier calls
+  if (sc) TNB_TRY(comm_barrier(h, st));
   const long long stride2 = (long long)(vbytes / 16);
   auto V = [&](int j) { return (void*)((char*)Vb + (size_t)j * vbytes); };
   const int grid = vec_grid(h, n2);
@@ -443,7 +479,16 @@ int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, co
     scale_inv_dev_kernel<<<grid, 256, 0, st>>>((double2*)V(0), (const double2*)phi, n2, scal, S_NRM, 0.0, tail);
     h->launches++;
     for (int j = 0; j < krylovdim; ++j) {
-      TNB_TRY(heff_core(h, dtype, d, d->chiL, L, W1, W2, R, V(j), w, t0, t1, st));
+      if (sc) {
+        // slab of H*v_j computed here, stored by the step-4 epilogue into EVERY rank's buffer (NVLink peer stores);
+        // buffers alternate so that a fast rank's next matvec cannot overwrite a vector a slow rank still works on
+        void* const* ob = sc->out[nmv & 1];
+        TNB_TRY(heff_shard_fused_core(h, dtype, d, h->comm.rank, h->comm.world, sc->clp, L, W1, W2, R, V(j), ob, t0, t1, st));
+        TNB_TRY(comm_barrier(h, st));
+        w = ob[h->comm.rank];
+      } else {
+        TNB_TRY(heff_core(h, dtype, d, d->chiL, L, W1, W2, R, V(j), w, t0, t1, st));
+      }
       ++nmv;
       // alpha_j = Re <v_j, w>
       TNB_TRY(dot_impl(h, dtype, n, V(j), w, scal + S_OVL, st));

@@ -18,6 +18,7 @@
 #include "tnb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -548,7 +549,9 @@ size_t stedc_ws_bytes(int64_t n) {
 // d (n), e (n-1) on the device; both are destroyed.  On return *Qres points at the n x n eigenvector
 // matrix (ld n, arena memory), *dres at the eigenvalue of each column and *idxres at the ascending order.
 int stedc_impl(Handle* h, int64_t n, double* d, double* e, double** Qres, double** dres, int** idxres, cudaStream_t st) {
-  if (n > 14000) return set_err(h, TNB_ERR_UNSUPPORTED, "stedc: n = %lld > 14000", (long long)n);
+  // Index arithmetic is int / n*n fits size_t; merges larger than 13824 rows (216 KB of shared memory for d and z)
+  // keep the deflation scan's working vectors in global memory instead.  32768 bounds the 4 n^2 workspace at 34 GB.
+  if (n > 32768) return set_err(h, TNB_ERR_UNSUPPORTED, "stedc: n = %lld > 32768", (long long)n);
   int L = 1;
   while ((n + L - 1) / L > DC_LEAF) L *= 2;
   std::vector<int> bounds(L + 1);
@@ -628,7 +631,8 @@ int stedc_impl(Handle* h, int64_t n, double* d, double* e, double** Qres, double
     int maxN = 0;
     for (int m = 0; m < nm; ++m) maxN = std::max(maxN, hN[off + m]);
     const size_t smem = (size_t)maxN * 16;
-    const int use_smem = smem <= 216 * 1024;
+    static const bool force_global = getenv("TNB_DC_NOSMEM") != nullptr;    // test hook for the large-merge path
+    const int use_smem = smem <= 216 * 1024 && !force_global;
     dc_m1_kernel<<<nm, 1024, use_smem ? smem : 0, st>>>(B, Qin, e, use_smem);
     h->launches++;
     TNB_CUDA(h, cudaMemcpyAsync(hk.data(), B.kcnt, nm * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -49,6 +49,22 @@ struct GemmParams {
   void* peerC[TNB_MAX_PEERS];
 };
 
+// Peer group of one NVSwitch node (one process per GPU): flag arrays of every rank mapped through CUDA IPC.  The
+// library numbers its own barrier epochs; every rank must issue the same sequence of collective calls.
+struct Comm {
+  bool on = false;
+  int rank = 0, world = 1;
+  unsigned long long* flags[TNB_MAX_PEERS] = {};
+  unsigned long long epoch = 0;
+};
+
+// Sharded matvec context of the Lanczos solver: this rank owns the slab L[:, l'_shard, :] (clp columns) and the
+// result of matvec number i lands, through the fused all-gather, in out[i & 1][g] of every rank g.
+struct ShardCtx {
+  int64_t clp;
+  void* const* out[2];
+};
+
 struct Handle {
   int device = 0;
   int num_sms = 148;
@@ -65,6 +81,7 @@ struct Handle {
   unsigned* counter = nullptr;  // last-block-done ticket (self-resetting)
   void* what = nullptr;         // combined two-site MPO matrix of the fused H_eff step 2+3 (64 KB)
   cudaEvent_t ev[16] = {};      // chunk hand-over events of the pipelined host-buffer H_eff (created on first use)
+  Comm comm;                    // peer group (tnb_comm_init)
 };
 constexpr int RED_MAX_BLOCKS = 1024;
 
@@ -141,7 +158,20 @@ int env_update_impl(Handle* h, int dtype, bool left, int64_t cl, int64_t cr, int
                     cudaStream_t st);
 int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
                  const void* W2, const void* R, void* phi, int krylovdim, int maxiter, double tol,
-                 double* energy, int* n_matvec, cudaStream_t st);
+                 double* energy, int* n_matvec, cudaStream_t st, const ShardCtx* sc = nullptr);
+// sharded H_eff*phi with the all-gather fused into step 4 (peer stores), no barrier
+int heff_shard_fused_core(Handle* h, int dtype, const tnb_bond_dims* d, int rank, int world, int64_t clp,
+                          const void* Lslab, const void* W1, const void* W2, const void* R, const void* phi,
+                          void* const* out_peers, void* t0, void* t1, cudaStream_t st);
+size_t heff_shard_ws_bytes(int dtype, const tnb_bond_dims* d, int64_t clp);
+// device-side barrier over the handle's peer group (stream-ordered, asynchronous)
+int comm_barrier(Handle* h, cudaStream_t st);
+// barrier; region [off + rank*bytes, +bytes) of bufs[rank] -> same region of every peer buffer; barrier
+int comm_allgather(Handle* h, void* const* bufs, size_t off, size_t bytes_per_rank, cudaStream_t st);
+int factorize_core_pub(Handle* h, int dtype, int64_t m, int64_t n, void* M, int ortho, int which, int64_t maxdim,
+                       int64_t mindim, double cutoff, const void* rho_pert, int normalize, void* A, void* B,
+                       int64_t* n_keep, double* truncerr, cudaStream_t st);
+size_t factorize_ws_bytes_pub(int dtype, int64_t m, int64_t n);
 int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1,
                     const void* W2, const void* R, const void* phi, int ortho, double noise,
                     int accumulate, void* rho, void* t0, void* t1, cudaStream_t st);

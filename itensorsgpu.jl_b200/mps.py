@@ -125,7 +125,8 @@ def inner(phi, psi, H=None):
     """<phi|psi> or <phi|H|psi> (``test/test_cumps.jl:71-101``, ``test/test_cumpo.jl:42-91``)."""
     if len(phi) != len(psi) or (H is not None and len(H) != len(psi)):
         raise _lib.DimensionMismatch(2, "inner: chains of different length")
-    cplx = any(t.dtype == torch.complex128 for t in list(phi.tensors) + list(psi.tensors))
+    cplx = any(t.dtype == torch.complex128 for t in list(phi.tensors) + list(psi.tensors) +
+               (list(H.tensors) if H is not None else []))
     dt = torch.complex128 if cplx else torch.float64
     if H is None:
         E = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1))
@@ -319,11 +320,19 @@ class _EnvCache:
         return self.dev[j]
 
 
-def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None, env_store="device"):
+def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None, env_store="device",
+         comm=None, shard_min_chi=256, verify_ranks=False):
     """``energy, psi = dmrg(H, psi0, sweeps)`` ([EXT] ITensors 0.2 two-site DMRG; reference call sites
     ``examples/dmrg.jl:25``, ``test/dmrg.jl:27,75``).  Per bond: ONE fused C call (phi = A1*A2, Lanczos with
     krylovdim matvecs, optional noise term, truncated factorization) plus one environment update.
-    ``env_store="host"`` spills the environment cache to pinned host memory (see ``_EnvCache``)."""
+    ``env_store="host"`` spills the environment cache to pinned host memory (see ``_EnvCache``).
+
+    ``comm`` (a ``shard.ShardComm``; one process per GPU, every rank calls dmrg with the same arguments): the
+    matvecs, the noise term's big contractions and the environment updates of every bond whose left bond dimension
+    is divisible by the number of ranks and >= ``shard_min_chi`` are sharded over the output bond (``shard.ShardedSweep``);
+    the factorization is replicated.  Energies and the MPS are bit-identical on every rank and equal to the 1-GPU
+    sweep's up to the summation order of the sharded GEMMs (tests: 1e-12).  ``verify_ranks`` cross-checks
+    (energy, n_keep) over the ranks after every bond."""
     if not (H.on_gpu and psi0.on_gpu):
         raise _lib.TnbError(3, "dmrg: move H and psi0 to the GPU with cu(); there is no CPU path")
     N = len(psi0)
@@ -336,11 +345,32 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
     ts = [t.astype(dt) for t in ts]
     Ws = [w.astype(dt) for w in Ws]
     one = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1, 1))
+    sh = None
+    if comm is not None and comm.world > 1:
+        from .shard import ShardedSweep
+        chi_max = max([max(sweeps.maxdim)] + [t.dims[2] for t in ts])
+        sh = ShardedSweep(comm, dt, chi_max, max(t.dims[1] for t in ts), max(max(w.dims[0], w.dims[3]) for w in Ws),
+                          min_chi=shard_min_chi)
+    env_l = sh.env_left if sh else ops.env_update_left
+    env_r = sh.env_right if sh else ops.env_update_right
+
+    def bond_step(L, W1, W2, R, A1, A2, ortho, **kw):
+        if sh is None:
+            return ops.dmrg_bond_step(L, W1, W2, R, A1, A2, ortho, **kw)
+        out = sh.bond_step(L, W1, W2, R, A1, A2, ortho, **kw)
+        if verify_ranks:
+            import torch.distributed as dist
+            seen = [None] * comm.world
+            dist.all_gather_object(seen, (out[0], out[1].dims, out[3]), group=comm.group)
+            if any(x != seen[0] for x in seen):
+                raise _lib.TnbError(5, "dmrg: ranks diverged at a bond step: %r" % (seen,))
+        return out
+
     Rs = _EnvCache(N, env_store)
     Ls = _EnvCache(N, env_store)
     Rs.put(N - 1, one)
     for j in range(N - 1, 1, -1):
-        Rs.put(j - 1, ops.env_update_right(Rs.get(j), ts[j], Ws[j]))
+        Rs.put(j - 1, env_r(Rs.get(j), ts[j], Ws[j]))
         if j < N - 1:
             Rs.evict(j)
     Ls.put(0, one)
@@ -351,9 +381,8 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
         maxerr = 0.0
         for b in range(0, N - 1):
             Rs.prefetch(b + 2)                      # the next bond's right environment, one bond ahead
-            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls.get(b), Ws[b], Ws[b + 1], Rs.get(b + 1), ts[b], ts[b + 1],
-                                                               "left", **kw)
-            Ls.put(b + 1, ops.env_update_left(Ls.get(b), ts[b], Ws[b]))
+            energy, ts[b], ts[b + 1], err = bond_step(Ls.get(b), Ws[b], Ws[b + 1], Rs.get(b + 1), ts[b], ts[b + 1], "left", **kw)
+            Ls.put(b + 1, env_l(Ls.get(b), ts[b], Ws[b]))
             if b + 1 < N - 1:
                 Rs.drop(b + 1)        # stale now (site b+1 changed): one environment per bond stays alive
             if b > 0:
@@ -363,9 +392,8 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
                 observer(sw, b, "left", energy, err)
         for b in range(N - 2, -1, -1):
             Ls.prefetch(b - 1)
-            energy, ts[b], ts[b + 1], err = ops.dmrg_bond_step(Ls.get(b), Ws[b], Ws[b + 1], Rs.get(b + 1), ts[b], ts[b + 1],
-                                                               "right", **kw)
-            Rs.put(b, ops.env_update_right(Rs.get(b + 1), ts[b + 1], Ws[b + 1]))
+            energy, ts[b], ts[b + 1], err = bond_step(Ls.get(b), Ws[b], Ws[b + 1], Rs.get(b + 1), ts[b], ts[b + 1], "right", **kw)
+            Rs.put(b, env_r(Rs.get(b + 1), ts[b + 1], Ws[b + 1]))
             if b > 0:
                 Ls.drop(b)
             if b + 1 < N - 1:
@@ -376,7 +404,10 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
         if outputlevel > 0:
             print("After sweep %d energy=%.12f maxlinkdim=%d maxerr=%.2E" %
                   (sw + 1, energy, max(t.dims[2] for t in ts[:-1]), maxerr))
-    return energy, MPS(ts, llim=-1, rlim=1)
+    out = MPS(ts, llim=-1, rlim=1)
+    if sh is not None:
+        out.shard_stats = {"sharded_bond_steps": sh.sharded_steps, "replicated_bond_steps": sh.replicated_steps}
+    return energy, out
 
 
 def apply(gates, psi, cutoff=None, maxdim=None):

@@ -99,7 +99,11 @@ class DTensor:
         return DTensor(torch.zeros(n, dtype=dtype, device=device), dims)
 
     def astype(self, dtype):
-        return self if self.data.dtype == dtype else DTensor(self.data.to(dtype), self.dims)
+        if self.data.dtype == dtype:
+            return self
+        if self.data.is_complex() and not dtype.is_complex:
+            raise TypeError("astype: refusing to drop the imaginary part of a complex tensor")
+        return DTensor(self.data.to(dtype), self.dims)
 
     def clone(self):
         return DTensor(self.data.clone(), self.dims)
@@ -377,7 +381,7 @@ def factorize_bond(phi, ortho="left", which_decomp=None, maxdim=None, mindim=1, 
     h = _lib.handle()
     cl, d1, d2, cr = phi.dims
     m, n = cl * d1, d2 * cr
-    if which_decomp == "eigen" or (which_decomp is None and (rho_pert is not None or (cutoff or 0.0) > 1e-12)):
+    if which_decomp == "eigen" or (which_decomp in (None, "automatic") and (rho_pert is not None or (cutoff or 0.0) > 1e-12)):
         rfull = m if ortho == "left" else n
     else:
         rfull = min(m, n)
@@ -407,7 +411,7 @@ def dmrg_bond_step(L, W1, W2, R, A1, A2, ortho, maxdim, mindim=1, cutoff=0.0, no
     if cm != cm2:
         raise _lib.DimensionMismatch(2, "A1/A2 middle bond differs")
     m, n = cl * d1, d2 * cr
-    use_eigen = which_decomp == "eigen" or (which_decomp is None and (noise > 0 or (cutoff or 0.0) > 1e-12))
+    use_eigen = which_decomp == "eigen" or (which_decomp in (None, "automatic") and (noise > 0 or (cutoff or 0.0) > 1e-12))
     rfull = (m if ortho == "left" else n) if use_eigen else min(m, n)
     kmax = max(1, min(rfull, int(maxdim)))
     bd = BondDims(cl, cr, d1, d2, W1.dims[0], W1.dims[3], W2.dims[3])

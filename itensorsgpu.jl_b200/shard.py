@@ -204,10 +204,18 @@ class MpoSplitHeff:
             ops.contract(T2, ("s2", "r", "lp", "s1p", "b"), self.W2, ("b", "s2", "s2p", "c"),
                          lc=("r", "lp", "s1p", "s2p", "c"), out=DTensor(Z, (cr, cl, d1, d2, self.wr)))
         # reduce every c-chunk to its owner (unequal chunk sizes: one reduce per destination)
+        staged = dist.get_backend(self.group) == "gloo"     # gloo (ranks sharing a GPU in the tests) reduces on the host
         work = []
         for g, (c0, c1) in enumerate(self.cr_):
             if c1 > c0:
-                work.append(dist.reduce(Z[c0 * npl: c1 * npl], dst=g, group=self.group, async_op=True))
+                if staged:
+                    hz = Z[c0 * npl: c1 * npl].cpu()
+                    hz = torch.view_as_real(hz) if hz.is_complex() else hz
+                    dist.reduce(hz, dst=g, group=self.group)
+                    if g == self.rank:
+                        Z[c0 * npl: c1 * npl].copy_(torch.view_as_complex(hz) if Z.is_complex() else hz)
+                else:
+                    work.append(dist.reduce(Z[c0 * npl: c1 * npl], dst=g, group=self.group, async_op=True))
         for wk in work:
             wk.wait()
         out = torch.zeros(cl * d1 * d2 * cr, dtype=phi.dtype, device=phi.data.device)
@@ -216,5 +224,218 @@ class MpoSplitHeff:
             Zs = DTensor(Z[c0 * npl: c1 * npl], (cr, cl, d1, d2, c1 - c0))
             ops.contract(Zs, ("r", "lp", "s1p", "s2p", "c"), self.Rs, ("r", "rp", "c"), lc=("lp", "s1p", "s2p", "rp"),
                          out=DTensor(out, (cl, d1, d2, cr)))
-        dist.all_reduce(out, group=self.group)
+        if staged:
+            ho = out.cpu()
+            hr = torch.view_as_real(ho) if ho.is_complex() else ho
+            dist.all_reduce(hr, group=self.group)
+            out.copy_(ho)
+        else:
+            dist.all_reduce(out, group=self.group)
         return DTensor(out, (cl, d1, d2, cr))
+
+
+# ---------------------------------------------------------------------------------------------
+# Peer group on the handle (tnb_comm_init) and the sharded DMRG sweep built on it
+# ---------------------------------------------------------------------------------------------
+class ShardComm:
+    """The peer group of this process (one process per GPU; ``torch.distributed`` is used only to exchange the
+    64-byte IPC handles and for host-side barriers -- gloo or nccl).  Registers the peer-mapped flag arrays on the
+    library handle; after that every collective step of the sharded path is a device-side barrier, a peer store
+    from a GEMM epilogue or a copy-engine write into a peer-mapped buffer."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        from . import _lib
+        self.h = _lib.handle()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.flags = PeerBuffers(256, group)
+        self.h.check(self.h.lib.tnb_comm_init(self.h.h, self.rank, self.world, self.flags.c_array()))
+        self._bufs = {}
+
+    def buffer(self, name, nbytes):
+        """Peer-mapped buffer set ``name`` of at least ``nbytes`` per rank (collective: every rank must ask for the
+        same names and sizes in the same order)."""
+        b = self._bufs.get(name)
+        if b is not None and b.nbytes >= nbytes:
+            return b
+        if b is not None:
+            b.close()
+        b = PeerBuffers(int(nbytes), self.group)
+        self._bufs[name] = b
+        return b
+
+    def barrier(self):
+        from . import ops
+        self.h.check(self.h.lib.tnb_comm_barrier(self.h.h, ops._stream()))
+
+    def allgather(self, bufs, nbytes_per_rank, offset=0):
+        from . import ops
+        self.h.check(self.h.lib.tnb_comm_allgather(self.h.h, bufs.c_array(), int(offset), int(nbytes_per_rank), ops._stream()))
+
+    def status(self):
+        from . import ops
+        self.h.check(self.h.lib.tnb_peer_status(self.h.h, ops._stream()))
+
+    def close(self):
+        torch.cuda.synchronize()
+        for b in self._bufs.values():
+            b.close()
+        self._bufs = {}
+        self.h.lib.tnb_comm_finalize(self.h.h)
+        self.flags.close()
+
+
+class ShardedHeffHost:
+    """End-to-end sharded H_eff*phi with HOST buffers (``tnb_heff_apply_shard_host``): each rank moves 1/world of phi
+    up and 1/world of H*phi down over PCIe; the rest crosses NVLink."""
+
+    def __init__(self, comm, phi_dims, dtype=torch.float64):
+        n = 1
+        for d in phi_dims:
+            n *= int(d)
+        es = 16 if dtype == torch.complex128 else 8
+        self.comm, self.dims, self.dtype = comm, tuple(phi_dims), dtype
+        self.phis = comm.buffer("e2e_phi", n * es)
+        self.outs = comm.buffer("e2e_out", n * es)
+
+    def apply_host(self, Lslab, W1, W2, R, phi_host, out_host):
+        """phi_host / out_host: pinned CPU tensors in phi's layout; only this rank's r-chunk of phi_host is read and
+        only its l' slab of out_host is written.  Synchronous."""
+        import ctypes as C
+        from . import ops
+        from .ops import BondDims
+        h = self.comm.h
+        cl, d1, d2, cr = self.dims
+        bd = BondDims(cl, cr, d1, d2, W1.dims[0], W1.dims[3], W2.dims[3])
+        h.check(h.lib.tnb_heff_apply_shard_host(h.h, ops._dt(Lslab.data), C.byref(bd), ops._ptr(Lslab.data), ops._ptr(W1.data),
+                                                ops._ptr(W2.data), ops._ptr(R.data), ops._ptr(phi_host), self.phis.c_array(),
+                                                self.outs.c_array(), ops._ptr(out_host), ops._stream()))
+        return out_host
+
+    def device_result(self):
+        """DTensor view of the full H*phi in this rank's own result buffer (after apply_host)."""
+        from .ops import DTensor
+        n = 1
+        for d in self.dims:
+            n *= d
+        return DTensor(self.outs.local(self.dtype)[:n], self.dims)
+
+
+def _env_kind(E):
+    return "slab" if E.dims[0] != E.dims[1] else "full"
+
+
+class ShardedSweep:
+    """Per-bond operations of a multi-GPU two-site DMRG sweep (used by ``mps.dmrg(..., comm=...)``).
+
+    Left environments of bonds whose dimension is divisible by the number of ranks (and at least ``min_chi``) are
+    kept as l' slabs -- 1/world of the memory, never moved; smaller ones and all right environments are replicated.
+    On a sharded bond the three Lanczos matvecs, the noise term's big contractions and both environment updates run
+    at 1/world of the flops per rank; the truncated factorization is replicated (deterministic kernels, identical
+    inputs), so the MPS stays bit-identical on every rank without a broadcast."""
+
+    def __init__(self, comm, dtype, chi_max, d, w, min_chi=256):
+        self.comm, self.dtype = comm, dtype
+        self.world, self.rank = comm.world, comm.rank
+        self.min_chi = max(int(min_chi), self.world)
+        es = 16 if dtype == torch.complex128 else 8
+        h = comm.h
+        n = int(chi_max) * int(chi_max) * d * d
+        self.out_a = comm.buffer("lanczos_a", n * es)
+        self.out_b = comm.buffer("lanczos_b", n * es)
+        self.stage = comm.buffer("stage", int(h.lib.tnb_shard_stage_bytes(1 if es == 16 else 0, int(chi_max), d, w, self.world)))
+        self.sharded_steps = 0
+        self.replicated_steps = 0
+
+    def shardable(self, chi):
+        return chi % self.world == 0 and chi >= self.min_chi
+
+    # ---- layout conversions (rare: only where the chain's bond dimension crosses min_chi)
+    def to_slab(self, L):
+        from .ops import DTensor
+        if _env_kind(L) == "slab":
+            return L
+        cl, _, w = L.dims
+        lo, hi = slab_range(cl, self.rank, self.world)
+        return DTensor(left_env_slab(L.data, cl, w, self.rank, self.world), (cl, hi - lo, w))
+
+    def to_full(self, Ls):
+        """all-gather the l' slabs of a left environment into the replicated full tensor"""
+        from .ops import DTensor
+        if _env_kind(Ls) == "full":
+            return Ls
+        cl, clp, w = Ls.dims
+        es = Ls.data.element_size()
+        nb = Ls.data.numel() * es
+        mine = self.stage.local(Ls.dtype)
+        mine[self.rank * Ls.data.numel(): (self.rank + 1) * Ls.data.numel()].copy_(Ls.data)
+        self.comm.allgather(self.stage, nb)
+        g = mine[: self.world * Ls.data.numel()].view(self.world, w, clp, cl)           # [g][a][l'_s][l]
+        return DTensor(g.permute(1, 0, 2, 3).contiguous().reshape(-1), (cl, cl, w))      # [a][(g,l'_s)][l]
+
+    # ---- one bond
+    def bond_step(self, L, W1, W2, R, A1, A2, ortho, maxdim, mindim, cutoff, noise, krylovdim, maxiter, which_decomp):
+        import ctypes as C
+        from . import ops
+        from .ops import DTensor, BondDims
+        cl, d1, cm = A1.dims
+        _, d2, cr = A2.dims
+        sharded = _env_kind(L) == "slab" and (noise <= 0 or ortho == "left" or cr % self.world == 0)
+        if not sharded:
+            self.replicated_steps += 1
+            return ops.dmrg_bond_step(self.to_full(L), W1, W2, R, A1, A2, ortho, maxdim=maxdim, mindim=mindim, cutoff=cutoff,
+                                      noise=noise, krylovdim=krylovdim, maxiter=maxiter, which_decomp=which_decomp)
+        self.sharded_steps += 1
+        h = self.comm.h
+        m, n = cl * d1, d2 * cr
+        use_eigen = which_decomp == "eigen" or (which_decomp in (None, "automatic") and (noise > 0 or (cutoff or 0.0) > 1e-12))
+        rfull = (m if ortho == "left" else n) if use_eigen else min(m, n)
+        kmax = max(1, min(rfull, int(maxdim)))
+        bd = BondDims(cl, cr, d1, d2, W1.dims[0], W1.dims[3], W2.dims[3])
+        dev = A1.data.device
+        b1 = torch.empty(max(A1.size, m * kmax), dtype=A1.dtype, device=dev)
+        b2 = torch.empty(max(A2.size, kmax * n), dtype=A2.dtype, device=dev)
+        b1[: A1.size].copy_(A1.data)
+        b2[: A2.size].copy_(A2.data)
+        e = C.c_double(0.0)
+        nk = C.c_int64(0)
+        err = C.c_double(0.0)
+        h.check(h.lib.tnb_dmrg_bond_step_shard(h.h, ops._dt(A1.data), C.byref(bd), cm, ops._ptr(L.data), ops._ptr(W1.data),
+                                               ops._ptr(W2.data), ops._ptr(R.data), ops._ptr(b1), ops._ptr(b2),
+                                               0 if ortho == "left" else 1, ops._DECOMP[which_decomp], int(maxdim), int(mindim),
+                                               float(cutoff or 0.0), float(noise), int(krylovdim), int(maxiter),
+                                               self.out_a.c_array(), self.out_b.c_array(), self.stage.c_array(),
+                                               C.byref(e), C.byref(nk), C.byref(err), ops._stream()))
+        k = nk.value
+        return e.value, DTensor(b1[: m * k], (cl, d1, k)), DTensor(b2[: k * n], (k, d2, cr)), err.value
+
+    def env_left(self, L, A, W):
+        """new left environment for the bond to the right of site tensor A (slab if that bond is shardable)"""
+        from . import ops
+        from .ops import DTensor
+        cl, d, cr = A.dims
+        want_slab = self.shardable(cr)
+        if want_slab and _env_kind(L) == "slab":
+            h = self.comm.h
+            out = DTensor.empty((cr, cr // self.world, W.dims[3]), A.dtype, A.data.device)
+            h.check(h.lib.tnb_env_update_left_shard(h.h, ops._dt(A.data), cl, cr, d, W.dims[0], W.dims[3], ops._ptr(L.data),
+                                                    ops._ptr(A.data), ops._ptr(W.data), self.stage.c_array(),
+                                                    ops._ptr(out.data), ops._stream()))
+            return out
+        full = ops.env_update_left(self.to_full(L), A, W)
+        return self.to_slab(full) if want_slab else full
+
+    def env_right(self, R, A, W):
+        """new (replicated) right environment for the bond to the left of site tensor A"""
+        from . import ops
+        from .ops import DTensor
+        cl, d, cr = A.dims
+        if self.shardable(cl) and self.shardable(cr):
+            h = self.comm.h
+            out = DTensor.empty((cl, cl, W.dims[0]), A.dtype, A.data.device)
+            h.check(h.lib.tnb_env_update_right_shard(h.h, ops._dt(A.data), cl, cr, d, W.dims[0], W.dims[3], ops._ptr(R.data),
+                                                     ops._ptr(A.data), ops._ptr(W.data), self.stage.c_array(),
+                                                     ops._ptr(out.data), ops._stream()))
+            return out
+        return ops.env_update_right(R, A, W)

@@ -103,6 +103,8 @@ class ShardedTEBD:
         self.N = N
         self.state = state
         self.gate_fn = gate_fn or ops.tebd_gate_bform
+        # gloo moves host memory only (CPU plumbing test; ranks sharing one GPU in the -m gpu tests): stage through the host
+        self.staged = dist.get_backend(group) == "gloo"
         lo, hi = block_range(N, self.rank, self.world)
         if state.first != lo or len(state) != hi - lo:
             raise _lib.DimensionMismatch(2, "rank %d holds sites [%d,%d), expected [%d,%d)" %
@@ -122,31 +124,38 @@ class ShardedTEBD:
         cplx = t.data.is_complex()
         hdr = torch.tensor(list(t.dims) + [1 if cplx else 0], dtype=torch.int64, device=t.data.device)
         payload = torch.view_as_real(t.data).reshape(-1) if cplx else t.data
+        if self.staged:
+            hdr, payload = hdr.cpu(), payload.cpu()
         return [d.isend(hdr, dst, group=self.group), d.isend(payload.contiguous(), dst, group=self.group)]
 
     def _recv_tensor(self, src, device):
         d = self.dist
-        hdr = torch.empty(4, dtype=torch.int64, device=device)
+        rdev = "cpu" if self.staged else device
+        hdr = torch.empty(4, dtype=torch.int64, device=rdev)
         d.recv(hdr, src, group=self.group)
         a, b, c, cplx = [int(x) for x in hdr.tolist()]
         n = a * b * c
-        buf = torch.empty(2 * n if cplx else n, dtype=torch.float64, device=device)
+        buf = torch.empty(2 * n if cplx else n, dtype=torch.float64, device=rdev)
         d.recv(buf, src, group=self.group)
+        buf = buf.to(device)
         data = torch.view_as_complex(buf.view(n, 2)) if cplx else buf
         return DTensor(data, (a, b, c))
 
     def _send_vec(self, v, dst):
         d = self.dist
         hdr = torch.tensor([v.numel()], dtype=torch.int64, device=v.device)
+        if self.staged:
+            hdr, v = hdr.cpu(), v.cpu()
         return [d.isend(hdr, dst, group=self.group), d.isend(v.contiguous(), dst, group=self.group)]
 
     def _recv_vec(self, src, device):
         d = self.dist
-        hdr = torch.empty(1, dtype=torch.int64, device=device)
+        rdev = "cpu" if self.staged else device
+        hdr = torch.empty(1, dtype=torch.int64, device=rdev)
         d.recv(hdr, src, group=self.group)
-        v = torch.empty(int(hdr.item()), dtype=torch.float64, device=device)
+        v = torch.empty(int(hdr.item()), dtype=torch.float64, device=rdev)
         d.recv(v, src, group=self.group)
-        return v
+        return v.to(device)
 
     def layer(self, G, parity, maxdim=None, cutoff=0.0):
         """One even (0) or odd (1) layer over the whole chain; returns this rank's largest truncation error."""

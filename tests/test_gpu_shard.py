@@ -33,18 +33,8 @@ def test_heff_apply_shard_slabs(world, cplx):
     assert ot.rel_err(full.cpu().numpy().reshape((chi, d, d, cr), order="F"), want) < 1e-12
 
 
-def _fused_worker(rank, world, port, q, cplx):
-    import os
-    import sys
+def _fused_worker(rank, world, cplx):
     import torch
-    import torch.distributed as dist
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, root)
-    sys.path.insert(0, os.path.join(root, "tests"))
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from itensorsgpu_b200 import tn
     rng = np.random.default_rng(52)
     chi, cr, d, w = 64, 48, 2, 5
@@ -62,46 +52,21 @@ def _fused_worker(rank, world, port, q, cplx):
         torch.cuda.synchronize()
         errs.append(ot.rel_err(out.numpy(), od.heff_apply(L, W1, W2, R, phi)))
     fh.status()
-    dist.barrier()
     fh.close()
-    q.put((rank, max(errs)))
-    dist.destroy_process_group()
+    return max(errs)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("cplx", [False, True])
-def test_heff_shard_fused_gather_two_gpus(cplx):
-    """GEMM + all-gather fused over NVLink peer memory (tnb_heff_apply_shard_fused): every rank must hold the full
-    H*phi after the call, with no NCCL data collective."""
-    import os
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29800 + (os.getpid() % 2000) + int(cplx)
-    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, q, cplx)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    assert all(e < 1e-12 for _, e in res)
+def test_heff_shard_fused_gather(world, cplx):
+    """GEMM + all-gather fused over peer memory (tnb_heff_apply_shard_fused): every rank must hold the full H*phi
+    after the call, with no library collective.  One rank per GPU when the box has enough GPUs, ranks sharing
+    GPUs otherwise (CUDA IPC works within one device too) -- never skipped."""
+    from mp_util import run_ranks
+    assert max(run_ranks(_fused_worker, world, cplx)) < 1e-12
 
 
-def _mpo_worker(rank, world, port, q):
-    import os
-    import sys
-    import torch
-    import torch.distributed as dist
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, root)
-    sys.path.insert(0, os.path.join(root, "tests"))
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+def _mpo_worker(rank, world):
     from itensorsgpu_b200 import tn
     rng = np.random.default_rng(53)
     chi, cr, d, w = 48, 40, 2, 5
@@ -114,28 +79,14 @@ def _mpo_worker(rank, world, port, q):
         ms = tn.shard.MpoSplitHeff(D(L), D(W1), D(W2), D(R))
         out = ms.apply(D(phi))
         errs.append(ot.rel_err(out.numpy(), od.heff_apply(L, W1, W2, R, phi)))
-    q.put((rank, max(errs)))
-    dist.destroy_process_group()
+    return max(errs)
 
 
-def test_heff_mpo_bond_split_two_gpus():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_heff_mpo_bond_split(world):
     """The north star's MPO-bond split (reduce of the c-planes + all-reduce of H*phi) against the oracle."""
-    import os
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29900 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_mpo_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    assert all(e < 1e-12 for _, e in res)
+    from mp_util import run_ranks
+    assert max(run_ranks(_mpo_worker, world)) < 1e-12
 
 
 def test_mpo_split_ranges():

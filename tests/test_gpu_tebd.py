@@ -83,17 +83,10 @@ def test_tebd_layers_match_apply(cplx):
     assert np.linalg.norm(c / np.linalg.norm(c) - a) < 1e-11
 
 
-def _worker(rank, world, port, q):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+def _worker(rank, world):
     from itensorsgpu_b200 import tn
     rng = np.random.default_rng(34)
-    N = 12
+    N = 4 * world + 4
     psi = omps.random_mps(N, 2, 8, rng, dtype=np.complex128)
     G = models.heisenberg_bond_gate(0.05, imaginary_time=False)
     Gd = tn.DTensor.from_numpy(G)
@@ -109,23 +102,13 @@ def _worker(rank, world, port, q):
         tn.tebd.tebd_layer(single, Gd, 1, maxdim=12)
     a = omps.to_dense([t.numpy() for t in out.Bs])
     b = omps.to_dense([t.numpy() for t in single.Bs])
-    q.put((rank, float(np.linalg.norm(a - b)), [t.dims for t in out.Bs] == [t.dims for t in single.Bs]))
-    dist.destroy_process_group()
+    return float(np.linalg.norm(a - b)), [t.dims for t in out.Bs] == [t.dims for t in single.Bs]
 
 
-def test_sharded_tebd_two_gpus():
-    """Two ranks / two GPUs over NCCL: identical state to the single-GPU layer loop (same kernels, same order)."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    assert all(e < 1e-12 and same for _, e, same in res)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_tebd_ranks(world):
+    """2 / 4 / 8 ranks (one per GPU when the box has them, sharing GPUs otherwise): identical state to the single-GPU
+    layer loop (same kernels, same order)."""
+    from mp_util import run_ranks
+    res = run_ranks(_worker, world)
+    assert all(e < 1e-12 and same for e, same in res)
