@@ -56,14 +56,8 @@ def _fused_worker(rank, world, cplx):
     return max(errs)
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("cplx", [False, True])
-def test_heff_shard_fused_gather(world, cplx):
-    """GEMM + all-gather fused over peer memory (tnb_heff_apply_shard_fused): every rank must hold the full H*phi
-    after the call, with no library collective.  One rank per GPU when the box has enough GPUs, ranks sharing
-    GPUs otherwise (CUDA IPC works within one device too) -- never skipped."""
-    from mp_util import run_ranks
-    assert max(run_ranks(_fused_worker, world, cplx)) < 1e-12
+# _fused_worker / _mpo_worker run at 2, 4 and 8 ranks inside tests/test_gpu_shard_dmrg.py::test_multi_rank_suite
+# (GEMM + all-gather fused over peer memory; every rank must hold the full H*phi with no library collective).
 
 
 def _mpo_worker(rank, world):
@@ -80,13 +74,6 @@ def _mpo_worker(rank, world):
         out = ms.apply(D(phi))
         errs.append(ot.rel_err(out.numpy(), od.heff_apply(L, W1, W2, R, phi)))
     return max(errs)
-
-
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_heff_mpo_bond_split(world):
-    """The north star's MPO-bond split (reduce of the c-planes + all-reduce of H*phi) against the oracle."""
-    from mp_util import run_ranks
-    assert max(run_ranks(_mpo_worker, world)) < 1e-12
 
 
 def test_mpo_split_ranges():

@@ -18,10 +18,9 @@ def _rand(rng, shape, cplx):
     return a
 
 
-def _w_allgather(rank, world):
+def _w_allgather(rank, world, comm):
     import torch
     from itensorsgpu_b200 import tn
-    comm = tn.shard.ShardComm()
     n = 1000
     bufs = comm.buffer("t", 8 * n * world + 4096)
     errs = 0
@@ -34,16 +33,10 @@ def _w_allgather(rank, world):
             want = torch.arange(n, dtype=torch.float64, device="cuda") + 1e6 * g + 1e3 * rep
             errs += int(not torch.equal(loc[g * n:(g + 1) * n], want))
     comm.status()
-    comm.close()
     return errs
 
 
-@pytest.mark.parametrize("world", WORLDS)
-def test_comm_allgather(world):
-    assert run_ranks(_w_allgather, world) == [0] * world
-
-
-def _w_env(rank, world, cplx):
+def _w_env(rank, world, comm, cplx):
     import torch
     from itensorsgpu_b200 import tn
     from oracle import dmrg as od
@@ -53,7 +46,6 @@ def _w_env(rank, world, cplx):
     A = _rand(rng, (cl, d, cr), cplx); W = _rand(rng, (wl, d, d, wr), cplx)
     L = _rand(rng, (cl, cl, wl), cplx); R = _rand(rng, (cr, cr, wr), cplx)
     D = tn.DTensor.from_numpy
-    comm = tn.shard.ShardComm()
     dt = torch.complex128 if cplx else torch.float64
     sh = tn.shard.ShardedSweep(comm, dt, max(cl, cr), d, max(wl, wr), min_chi=world)
     errs = []
@@ -68,17 +60,10 @@ def _w_env(rank, world, cplx):
         gotR = sh.env_right(D(R), D(A), D(W))
         errs.append(ot.rel_err(gotR.numpy(), od.env_right_update(R, A, W)))
     comm.status()
-    comm.close()
     return max(errs)
 
 
-@pytest.mark.parametrize("world", WORLDS)
-@pytest.mark.parametrize("cplx", [False, True])
-def test_env_updates_shard(world, cplx):
-    assert max(run_ranks(_w_env, world, cplx)) < 1e-12
-
-
-def _w_lanczos_and_host(rank, world, cplx):
+def _w_lanczos_and_host(rank, world, comm, cplx):
     import ctypes as C
     import torch
     from itensorsgpu_b200 import tn
@@ -93,7 +78,6 @@ def _w_lanczos_and_host(rank, world, cplx):
     phi = _rand(rng, (cl, d, d, cr), cplx)
     D = tn.DTensor.from_numpy
     dt = torch.complex128 if cplx else torch.float64
-    comm = tn.shard.ShardComm()
     sh = tn.shard.ShardedSweep(comm, dt, max(cl, cr), d, w, min_chi=world)
     Ls = sh.to_slab(D(L))
     # sharded Lanczos vs the single-GPU call on the same operands
@@ -122,17 +106,10 @@ def _w_lanczos_and_host(rank, world, cplx):
         errs.append(float(np.abs(got[mask]).max()) if mask.any() else 0.0)       # nothing outside the slab is written
         errs.append(ot.rel_err(hh.device_result().numpy(), want))                # the device copy is the full vector
     comm.status()
-    comm.close()
     return max(errs)
 
 
-@pytest.mark.parametrize("world", WORLDS)
-@pytest.mark.parametrize("cplx", [False, True])
-def test_lanczos_shard_and_host_matvec(world, cplx):
-    assert max(run_ranks(_w_lanczos_and_host, world, cplx)) < 1e-12
-
-
-def _w_dmrg(rank, world, noise):
+def _w_dmrg(rank, world, comm, noise):
     import torch
     from itensorsgpu_b200 import tn
     N, chi = 12, 8 * world
@@ -142,23 +119,52 @@ def _w_dmrg(rank, world, noise):
     sw = tn.Sweeps(2, **kw)
     ref = []
     e1, _ = tn.dmrg(H, psi0, sw, observer=lambda s, b, o, e, err: ref.append(e))
-    comm = tn.shard.ShardComm()
     got = []
     e2, psi = tn.dmrg(H, psi0, sw, comm=comm, shard_min_chi=world, verify_ranks=True,
                       observer=lambda s, b, o, e, err: got.append(e))
     stats = psi.shard_stats
     comm.status()
-    comm.close()
     dev = max(abs(a - b) for a, b in zip(ref, got))
     return dev, stats["sharded_bond_steps"], len(ref) == len(got), e2
 
 
+def _suite(rank, world):
+    """every multi-rank check in ONE process group (spawning 8 CUDA processes costs more than the checks)"""
+    import test_gpu_shard as tgs
+    import test_gpu_tebd as tgt
+    from itensorsgpu_b200 import tn
+    out = {}
+    for cplx in (False, True):
+        out["fused_gather_%s" % ("c128" if cplx else "f64")] = tgs._fused_worker(rank, world, cplx)
+    out["mpo_split"] = tgs._mpo_worker(rank, world)
+    out["tebd"] = tgt._worker(rank, world)
+    comm = tn.shard.ShardComm()
+    out["allgather_mismatches"] = _w_allgather(rank, world, comm)
+    for cplx in (False, True):
+        tag = "c128" if cplx else "f64"
+        out["env_updates_%s" % tag] = _w_env(rank, world, comm, cplx)
+        out["lanczos_host_%s" % tag] = _w_lanczos_and_host(rank, world, comm, cplx)
+    for noise in (False, True):
+        out["dmrg_noise" if noise else "dmrg_svd"] = _w_dmrg(rank, world, comm, noise)
+    comm.close()
+    return out
+
+
 @pytest.mark.parametrize("world", WORLDS)
-@pytest.mark.parametrize("noise", [False, True])
-def test_dmrg_sharded_matches_single_gpu(world, noise):
-    """Every bond energy of a 2-sweep multi-rank dmrg() equals the single-GPU sweep's to 1e-12, the ranks stay
-    bit-identical (verify_ranks) and the sharded code path is actually taken."""
-    res = run_ranks(_w_dmrg, world, noise, timeout=900)
-    for dev, nshard, same_len, _ in res:
-        assert same_len and dev < 1e-12 and nshard > 0
-    assert len({r[3] for r in res}) == 1            # identical final energy on every rank
+def test_multi_rank_suite(world):
+    """2, 4 and 8 ranks: fused GEMM + all-gather over peer memory (F64, C128), MPO-bond split, sharded TEBD layers,
+    all-gather over peer memory, sharded environment updates, sharded Lanczos + host-buffer matvec, and a 2-sweep
+    dmrg(comm=...) on both factorize branches: every bond energy equals the single-GPU sweep's to 1e-12, the ranks
+    stay bit-identical (verify_ranks) and the sharded code path is actually taken."""
+    res = run_ranks(_suite, world, timeout=1500)
+    for r in res:
+        for k in ("fused_gather_f64", "fused_gather_c128", "mpo_split", "env_updates_f64", "env_updates_c128",
+                  "lanczos_host_f64", "lanczos_host_c128"):
+            assert r[k] < 1e-12, (k, r[k])
+        assert r["allgather_mismatches"] == 0
+        assert r["tebd"][0] < 1e-12 and r["tebd"][1]
+        for k in ("dmrg_svd", "dmrg_noise"):
+            dev, nshard, same_len, _ = r[k]
+            assert same_len and dev < 1e-12 and nshard > 0, (k, r[k])
+    for k in ("dmrg_svd", "dmrg_noise"):
+        assert len({r[k][3] for r in res}) == 1            # identical final energy on every rank

@@ -105,10 +105,4 @@ def _worker(rank, world):
     return float(np.linalg.norm(a - b)), [t.dims for t in out.Bs] == [t.dims for t in single.Bs]
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_tebd_ranks(world):
-    """2 / 4 / 8 ranks (one per GPU when the box has them, sharing GPUs otherwise): identical state to the single-GPU
-    layer loop (same kernels, same order)."""
-    from mp_util import run_ranks
-    res = run_ranks(_worker, world)
-    assert all(e < 1e-12 and same for e, same in res)
+# _worker runs at 2, 4 and 8 ranks inside tests/test_gpu_shard_dmrg.py::test_multi_rank_suite
