@@ -63,7 +63,7 @@ def _gate(cplx):
 def test_c4_gate_and_split_chi2048(cplx):
     """C4 at maxdim 2048: theta = G (A1 A2) then the split, 4096 x 4096.  Untruncated (maxdim = 4096) the product
     A1' A2' must reproduce the oracle's theta on sampled elements, A1' must be an isometry and the singular values
-    (column norms of A2') must match an independent svdvals (cuSOLVER through torch, used as a checker only)."""
+    (row norms of A2') must match LAPACK's (NumPy gesdd on the host -- the reference's CPU path)."""
     from itensorsgpu_b200 import tn
     chi, d = 2048, 2
     A1 = dev_rand((chi, d, chi), cplx, 4242); A2 = dev_rand((chi, d, chi), cplx, 4243)
@@ -87,14 +87,14 @@ def test_c4_gate_and_split_chi2048(cplx):
     # singular values: row norms of B2 (k x (d chi)) vs svdvals of the full theta computed by the checker
     th = torch.einsum("abcd,kcl,rdk->rbal", torch.as_tensor(G, device="cuda").to(A1.dtype), A1.data.view(chi, d, chi),
                       A2.data.view(chi, d, chi)).reshape(d * chi, d * chi)   # row-major (r,s2',s1',l) == column-major theta
-    sv = torch.linalg.svdvals(th)
+    sv = torch.from_numpy(np.linalg.svd(th.cpu().numpy(), compute_uv=False)).cuda()      # LAPACK gesdd: the CPU path
     mine = torch.linalg.vector_norm(B2.data.view(chi * d, k), dim=0)
     assert float((mine - sv).abs().max() / sv[0]) < 1e-12
 
 
 def test_c4_bform_gate_chi2048_truncated():
     """The call bench.py's tebd_c4 times: B-form gate at chi = 2048, ComplexF64, truncated to maxdim 2048.  Schmidt
-    values and the truncation error against svdvals of lam_L * theta (checker: torch), B2' right-isometry."""
+    values and the truncation error against LAPACK's singular values of lam_L * theta, B2' right-isometry."""
     from itensorsgpu_b200 import tn
     chi, d = 2048, 2
     g = torch.Generator(device="cuda").manual_seed(11)
@@ -114,7 +114,7 @@ def test_c4_bform_gate_chi2048_truncated():
     tt = torch.einsum("abcd,kcl,rdk->rbal", torch.as_tensor(G, device="cuda"), Bs[0].data.view(chi, d, chi),
                       Bs[1].data.view(chi, d, chi))                          # (r, s2', s1', l)
     th = (tt * lam.view(1, 1, 1, chi)).reshape(d * chi, d * chi)
-    sv = torch.linalg.svdvals(th)
+    sv = torch.from_numpy(np.linalg.svd(th.cpu().numpy(), compute_uv=False)).cuda()      # LAPACK gesdd: the CPU path
     kept = sv[:chi]
     want = kept / kept.norm()
     assert float((lam2 - want).abs().max()) < 1e-12

@@ -81,13 +81,14 @@ def _w_lanczos_and_host(rank, world, comm, cplx):
     sh = tn.shard.ShardedSweep(comm, dt, max(cl, cr), d, w, min_chi=world)
     Ls = sh.to_slab(D(L))
     # sharded Lanczos vs the single-GPU call on the same operands
-    p1 = D(phi); e1, n1 = tn.ops.eigsolve_lanczos(D(L), D(W1), D(W2), D(R), p1)
+    dW1, dW2, dR = D(W1), D(W2), D(R)         # keep the device operands alive across the raw-pointer call below
+    p1 = D(phi); e1, n1 = tn.ops.eigsolve_lanczos(D(L), dW1, dW2, dR, p1)
     p2 = D(phi)
     h = comm.h
     bd = tn.ops.BondDims(cl, cr, d, d, w, w, w)
     e2 = C.c_double(0.0); n2 = C.c_int(0)
-    h.check(h.lib.tnb_eigsolve_lanczos_shard(h.h, tn.ops._dt(p2.data), C.byref(bd), tn.ops._ptr(Ls.data), tn.ops._ptr(D(W1).data),
-                                             tn.ops._ptr(D(W2).data), tn.ops._ptr(D(R).data), tn.ops._ptr(p2.data),
+    h.check(h.lib.tnb_eigsolve_lanczos_shard(h.h, tn.ops._dt(p2.data), C.byref(bd), tn.ops._ptr(Ls.data), tn.ops._ptr(dW1.data),
+                                             tn.ops._ptr(dW2.data), tn.ops._ptr(dR.data), tn.ops._ptr(p2.data),
                                              sh.out_a.c_array(), sh.out_b.c_array(), 3, 1, 1e-14, C.byref(e2), C.byref(n2),
                                              tn.ops._stream()))
     errs = [abs(e1 - e2.value) / abs(e1), ot.rel_err(p2.numpy(), p1.numpy()), float(n1 != n2.value)]
@@ -109,44 +110,106 @@ def _w_lanczos_and_host(rank, world, comm, cplx):
     return max(errs)
 
 
-def _w_dmrg(rank, world, comm, noise):
+def _w_bond_step(rank, world, comm, cplx):
+    """one bond step (both ortho sides, with and without the noise term) sharded vs single-GPU: energy, kept
+    dimension and the gauge-invariant product A1'*A2'"""
     import torch
     from itensorsgpu_b200 import tn
+    from oracle import tensor as ot
+    rng = np.random.default_rng(73)
+    cl, cm, cr, d, w = 8 * world, 8 * world, 16 * world, 2, 5
+    L = _rand(rng, (cl, cl, w), cplx); L = L + np.conj(np.transpose(L, (1, 0, 2)))
+    R = _rand(rng, (cr, cr, w), cplx); R = R + np.conj(np.transpose(R, (1, 0, 2)))
+    W1 = _rand(rng, (w, d, d, w), cplx); W1 = W1 + np.conj(np.transpose(W1, (0, 2, 1, 3)))
+    W2 = _rand(rng, (w, d, d, w), cplx); W2 = W2 + np.conj(np.transpose(W2, (0, 2, 1, 3)))
+    A1 = _rand(rng, (cl, d, cm), cplx); A2 = _rand(rng, (cm, d, cr), cplx)
+    D = tn.DTensor.from_numpy
+    dt = torch.complex128 if cplx else torch.float64
+    sh = tn.shard.ShardedSweep(comm, dt, max(cl, cr), d, w, min_chi=world)
+    dL, dW1, dW2, dR = D(L), D(W1), D(W2), D(R)
+    Ls = sh.to_slab(dL)
+    worst = 0.0
+    for ortho in ("left", "right"):
+        for noise, cutoff in ((0.0, 0.0), (1e-3, 1e-11), (0.0, 1e-11)):
+            kw = dict(maxdim=12 * world, mindim=1, cutoff=cutoff, noise=noise, krylovdim=3, maxiter=1, which_decomp=None)
+            e1, a1, a2, err1 = tn.ops.dmrg_bond_step(dL, dW1, dW2, dR, D(A1), D(A2), ortho, **kw)
+            e2, b1, b2, err2 = sh.bond_step(Ls, dW1, dW2, dR, D(A1), D(A2), ortho, **kw)
+            assert a1.dims == b1.dims and a2.dims == b2.dims, (a1.dims, b1.dims)
+            t1 = np.tensordot(a1.numpy(), a2.numpy(), axes=(2, 0)); t2 = np.tensordot(b1.numpy(), b2.numpy(), axes=(2, 0))
+            worst = max(worst, abs(e1 - e2) / abs(e1), ot.rel_err(t2, t1), abs(err1 - err2))
+    comm.status()
+    return worst
+
+
+def _w_dmrg(rank, world, comm, noise):
+    """3-sweep dmrg() sharded vs single-GPU on a chain WITHOUT degenerate multiplets (random site fields break SU(2):
+    where the maxdim cut falls inside a multiplet, which vectors survive depends on rounding and two correct
+    implementations separate by the truncation error -- tests/test_gpu_dmrg.py documents the same for GPU vs oracle).
+    Sweeps run with the noise term agree to O(noise) (the cut crosses a noise-dominated cluster); the last,
+    noise-free sweep is strict."""
+    from itensorsgpu_b200 import tn
     N, chi = 12, 8 * world
-    H = tn.cu(tn.heisenberg_mpo(N, 0.5))
+    Hh = tn.heisenberg_mpo(N, 0.5)
+    rng = np.random.default_rng(3)
+    Sz = np.diag([0.5, -0.5])
+    for j in range(N):
+        Wj = Hh.tensors[j].copy()
+        Wj[Wj.shape[0] - 1, :, :, 0] += 0.3 * rng.standard_normal() * Sz.T
+        Hh.tensors[j] = Wj
+    H = tn.cu(Hh)
     psi0 = tn.randomCuMPS(N, 2, chi=chi, seed=5)
-    kw = dict(maxdim=chi, cutoff=1e-11 if noise else 0.0, noise=1e-8 if noise else 0.0)
-    sw = tn.Sweeps(2, **kw)
-    ref = []
-    e1, _ = tn.dmrg(H, psi0, sw, observer=lambda s, b, o, e, err: ref.append(e))
-    got = []
+    # with the noise term the cut must not cross the noise-lifted cluster: cutoff 1e-7 >> noise (comment at the assert)
+    sw = tn.Sweeps(3, maxdim=chi, cutoff=0.0 if noise == 0.0 else 1e-7, noise=[noise, noise, 0.0])
+    ref, got = [], []
+    e1, _ = tn.dmrg(H, psi0, sw, observer=lambda s, b, o, e, err: ref.append((s, e)))
     e2, psi = tn.dmrg(H, psi0, sw, comm=comm, shard_min_chi=world, verify_ranks=True,
-                      observer=lambda s, b, o, e, err: got.append(e))
+                      observer=lambda s, b, o, e, err: got.append((s, e)))
     stats = psi.shard_stats
     comm.status()
-    dev = max(abs(a - b) for a, b in zip(ref, got))
-    return dev, stats["sharded_bond_steps"], len(ref) == len(got), e2
+    dev_noisy = max([abs(a[1] - b[1]) for a, b in zip(ref, got) if a[0] < 2] + [0.0])
+    dev_last = max(abs(a[1] - b[1]) for a, b in zip(ref, got) if a[0] == 2)
+    return dev_last, stats["sharded_bond_steps"], len(ref) == len(got), e2, dev_noisy
 
 
 def _suite(rank, world):
     """every multi-rank check in ONE process group (spawning 8 CUDA processes costs more than the checks)"""
+    import os
+    import time
     import test_gpu_shard as tgs
     import test_gpu_tebd as tgt
     from itensorsgpu_b200 import tn
     out = {}
+    trace = os.environ.get("TNB_TEST_TRACE")
+    t0 = time.time()
+
+    def mark(what):
+        if trace:
+            with open(os.path.join(trace, "suite_w%d_r%d.log" % (world, rank)), "a") as f:
+                f.write("%7.2f %s\n" % (time.time() - t0, what))
+    mark("start")
     for cplx in (False, True):
         out["fused_gather_%s" % ("c128" if cplx else "f64")] = tgs._fused_worker(rank, world, cplx)
+        mark("fused %s" % cplx)
     out["mpo_split"] = tgs._mpo_worker(rank, world)
+    mark("mpo")
     out["tebd"] = tgt._worker(rank, world)
+    mark("tebd")
     comm = tn.shard.ShardComm()
     out["allgather_mismatches"] = _w_allgather(rank, world, comm)
+    mark("allgather")
     for cplx in (False, True):
         tag = "c128" if cplx else "f64"
         out["env_updates_%s" % tag] = _w_env(rank, world, comm, cplx)
+        mark("env %s" % tag)
         out["lanczos_host_%s" % tag] = _w_lanczos_and_host(rank, world, comm, cplx)
-    for noise in (False, True):
+        mark("lanczos/host %s" % tag)
+        out["bond_step_%s" % tag] = _w_bond_step(rank, world, comm, cplx)
+        mark("bond step %s" % tag)
+    for noise in (0.0, 1e-9):
         out["dmrg_noise" if noise else "dmrg_svd"] = _w_dmrg(rank, world, comm, noise)
+        mark("dmrg noise=%g" % noise)
     comm.close()
+    mark("closed")
     return out
 
 
@@ -156,15 +219,24 @@ def test_multi_rank_suite(world):
     all-gather over peer memory, sharded environment updates, sharded Lanczos + host-buffer matvec, and a 2-sweep
     dmrg(comm=...) on both factorize branches: every bond energy equals the single-GPU sweep's to 1e-12, the ranks
     stay bit-identical (verify_ranks) and the sharded code path is actually taken."""
-    res = run_ranks(_suite, world, timeout=1500)
+    res = run_ranks(_suite, world, timeout=200)
     for r in res:
         for k in ("fused_gather_f64", "fused_gather_c128", "mpo_split", "env_updates_f64", "env_updates_c128",
                   "lanczos_host_f64", "lanczos_host_c128"):
             assert r[k] < 1e-12, (k, r[k])
+        for k in ("bond_step_f64", "bond_step_c128"):      # product of the factors of a truncated split: 1e-10
+            assert r[k] < 1e-10, (k, r[k])
         assert r["allgather_mismatches"] == 0
         assert r["tebd"][0] < 1e-12 and r["tebd"][1]
-        for k in ("dmrg_svd", "dmrg_noise"):
-            dev, nshard, same_len, _ = r[k]
-            assert same_len and dev < 1e-12 and nshard > 0, (k, r[k])
+        for k, noise in (("dmrg_svd", 0.0), ("dmrg_noise", 1e-9)):
+            dev_last, nshard, same_len, _, dev_noisy = r[k]
+            # Sharded and single-GPU sweeps must follow the SAME trajectory (1e-12 on every bond energy).  With the
+            # noise term this can only be asked when the cut does not cross the noise-lifted cluster of rho (eigenvalues
+            # ~ noise*|H phi|^2): a maxdim cut through that cluster picks different vectors on a rounding difference in
+            # the GEMM summation order and the two (equally valid) trajectories separate by far more than the noise --
+            # measured 1.7e-4 at 4 ranks.  The noise run therefore truncates by cutoff 1e-7 >> noise (eigen branch,
+            # maxdim not binding); the maxdim + noise combination is checked per step in _w_bond_step (1e-10).
+            tol_last, tol_noisy = 1e-12, 1e-12
+            assert same_len and dev_last < tol_last and dev_noisy < tol_noisy and nshard > 0, (k, r[k])
     for k in ("dmrg_svd", "dmrg_noise"):
         assert len({r[k][3] for r in res}) == 1            # identical final energy on every rank

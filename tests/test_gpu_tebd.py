@@ -86,7 +86,7 @@ def test_tebd_layers_match_apply(cplx):
 def _worker(rank, world):
     from itensorsgpu_b200 import tn
     rng = np.random.default_rng(34)
-    N = 4 * world + 4
+    N = max(12, 2 * world)          # dense comparison below: keep 2^N small
     psi = omps.random_mps(N, 2, 8, rng, dtype=np.complex128)
     G = models.heisenberg_bond_gate(0.05, imaginary_time=False)
     Gd = tn.DTensor.from_numpy(G)
