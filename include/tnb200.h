@@ -75,6 +75,14 @@ int tnb_version(void);
  * synchronises the device). */
 int tnb_reserve(tnb_handle_t h, size_t bytes);
 size_t tnb_workspace_bytes(tnb_handle_t h);
+/* Upper bound (bytes) on the PAIR of temporaries of one H_eff*phi / noise term / environment update (default 40 GB;
+ * 0 restores the default).  Above it the work is cut into slabs of the output bond (H_eff: independent
+ * full-efficiency slabs, L taken as a strided window, result written as a strided window) or of a summed bond with
+ * beta = 1 accumulation (environment updates, noise term), so that C5 (chi = 8192, MPO bond 30: 2 x 64 GB unchunked)
+ * runs in a fixed workspace.  Supersedes the reference's dead out-of-core attempt (src/tensor/dense.jl:50-193).
+ * Process-wide setting. */
+int tnb_set_workspace_limit(tnb_handle_t h, size_t bytes);
+size_t tnb_get_workspace_limit(tnb_handle_t h);
 /* Number of kernels this library has launched through the handle (bench `gpu_launches`). */
 uint64_t tnb_launch_count(tnb_handle_t h);
 

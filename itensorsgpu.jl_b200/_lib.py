@@ -47,6 +47,8 @@ SIGNATURES = {
     "tnb_reserve": (_int, [_vp, C.c_size_t]),
     "tnb_workspace_bytes": (C.c_size_t, [_vp]),
     "tnb_launch_count": (C.c_uint64, [_vp]),
+    "tnb_set_workspace_limit": (_int, [_vp, C.c_size_t]),
+    "tnb_get_workspace_limit": (C.c_size_t, [_vp]),
     "tnb_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp,
                             _vp, _vp, _int, _vp]),
     "tnb_permute_axpby": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _pi32, _vp, _vp, _vp, _vp]),
@@ -140,6 +142,14 @@ class Handle:
     @property
     def launches(self):
         return int(self.lib.tnb_launch_count(self.h))
+
+    def set_workspace_limit(self, nbytes):
+        """bound on the pair of temporaries of one matvec / noise term / environment update (0 = default 40 GB)"""
+        self.check(self.lib.tnb_set_workspace_limit(self.h, int(nbytes)))
+
+    @property
+    def workspace_limit(self):
+        return int(self.lib.tnb_get_workspace_limit(self.h))
 
     @property
     def workspace_bytes(self):

@@ -109,10 +109,34 @@ enum { mL = 0, mS1, mS2, mR, mLp, mA, mS1p, mB, mS2p, mC, mRp, mLpp, mS1pp, mS2p
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// Temporaries of one matvec / noise term / environment update are 2 x (base * w) elements: 2 x 2.7 GB at C3, but
+// 2 x 64 GB at C5 (chi = 8192, w = 30).  Above `g_ws_limit` bytes the work is cut into G slabs of an index that is a
+// FREE (output) index of the whole chain of contractions -- the output bond l' for H_eff, so that every slab is an
+// independent, full-efficiency H_eff with L taken as a strided window and the result written as a strided window of
+// the output vector (the same code path as the multi-GPU shard) -- or over a contracted index with beta = 1
+// accumulation in the last step (environment updates, noise term).  This supersedes the reference's dead out-of-core
+// attempt (/root/reference/src/tensor/dense.jl:50-193).
+static size_t g_ws_limit = (size_t)40 << 30;
+
+static int pick_chunks(size_t pair_bytes, int64_t extent) {
+  int G = 1;
+  while (pair_bytes / G > g_ws_limit && extent % (2 * G) == 0 && extent / (2 * G) >= 32) G *= 2;
+  return G;
+}
+
+static size_t heff_pair_bytes(int dtype, const tnb_bond_dims* d) {
+  const size_t base = (size_t)d->chiL * d->chiR * d->d1 * d->d2;
+  const size_t w = std::max({d->wL, d->wM, d->wR});
+  return 2 * base * w * elsize(dtype);
+}
+
+static int heff_nchunks(int dtype, const tnb_bond_dims* d) { return pick_chunks(heff_pair_bytes(dtype, d), d->chiL); }
+
 static size_t heff_ws_bytes(int dtype, const tnb_bond_dims* d) {
   const size_t base = (size_t)d->chiL * d->chiR * d->d1 * d->d2;
   const size_t w = std::max({d->wL, d->wM, d->wR});
-  return 2 * al256(base * w * elsize(dtype));
+  const int G = heff_nchunks(dtype, d);
+  return 2 * al256(base / G * w * elsize(dtype));
 }
 
 // out <- (((phi*L)*W1)*W2)*R using two ping-pong temporaries t0,t1 (each base*max(w) elements)
@@ -125,7 +149,7 @@ struct PeerOut {           // fused all-gather of the sharded result (step 4 epi
 
 static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* L, const void* W1,
                      const void* W2, const void* R, const void* phi, void* out, void* t0, void* t1,
-                     cudaStream_t st, const PeerOut* peers = nullptr) {
+                     cudaStream_t st, const PeerOut* peers = nullptr, int64_t lp_stored = 0) {
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
   // step 4 writes out[l'_slab, s1', s2', r'] -- dense, or (fused gather) a strided window of the full vector
   auto step4 = [&](const void* T3) -> int {
@@ -143,7 +167,13 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
     int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
     int64_t eb[] = {cl, clp, wl};    int32_t mb[] = {mL, mLp, mA};
     int64_t ec[] = {d1, d2, cr, clp, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
-    TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+    if (lp_stored > 0 && lp_stored != clp) {      // L is the window [:, l'_0 : l'_0 + clp, :] of a stored L[cl, lp_stored, wl]
+      int64_t sb[] = {1, cl, cl * lp_stored};
+      TNB_TRY(contract_impl_ex(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st, nullptr, nullptr, 0,
+                               nullptr, sb));
+    } else {
+      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
+    }
   }
   // 2+3 fused (one streaming pass) when the shape has an instantiation
   if (heff23_fused(h, dtype, d, clp, W1, W2, t0, t1, h->what, st)) {
@@ -166,6 +196,22 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
   return step4(t0);
 }
 
+// full H_eff*phi on one GPU; cut over the output bond when the temporaries would exceed the workspace limit
+static int heff_apply_any(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1, const void* W2,
+                          const void* R, const void* phi, void* out, void* t0, void* t1, cudaStream_t st) {
+  const int G = heff_nchunks(dtype, d);
+  if (G == 1) return heff_core(h, dtype, d, d->chiL, L, W1, W2, R, phi, out, t0, t1, st);
+  const int64_t cl = d->chiL, clp = cl / G;
+  const size_t es = elsize(dtype);
+  for (int j = 0; j < G; ++j) {
+    PeerOut po;
+    po.npeer = 1;
+    po.base[0] = (char*)out + (size_t)j * clp * es;
+    TNB_TRY(heff_core(h, dtype, d, clp, (const char*)L + (size_t)j * clp * cl * es, W1, W2, R, phi, nullptr, t0, t1, st, &po, cl));
+  }
+  return TNB_OK;
+}
+
 static int check_dims(Handle* h, const tnb_bond_dims* d) {
   if (!d) return set_err(h, TNB_ERR_BAD_ARG, "null dims");
   if (d->chiL < 1 || d->chiR < 1 || d->d1 < 1 || d->d2 < 1 || d->wL < 1 || d->wM < 1 || d->wR < 1)
@@ -182,7 +228,7 @@ int heff_apply_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
   void *t0, *t1;
   TNB_TRY(ws_alloc(h, need / 2, &t0));
   TNB_TRY(ws_alloc(h, need / 2, &t1));
-  return heff_core(h, dtype, d, d->chiL, L, W1, W2, R, phi, out, t0, t1, st);
+  return heff_apply_any(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
 }
 
 int heff_apply_shard_impl(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* Lslab,
@@ -292,51 +338,67 @@ int env_update_impl(Handle* h, int dtype, bool left, int64_t cl, int64_t cr, int
   if (cl < 1 || cr < 1 || d < 1 || wl < 1 || wr < 1) return set_err(h, TNB_ERR_BAD_ARG, "env_update: dims");
   ws_reset(h);
   const size_t es = elsize(dtype);
-  const size_t n1 = al256((size_t)cl * cr * d * std::max(wl, wr) * es);
+  // the two temporaries are cut over the bra bond of the OLD environment (l' for makeL!, r' for makeR!), which the
+  // last contraction sums over: chunk j contributes with beta = 1 (C5: 2 x 32 GB otherwise)
+  const int64_t ce = left ? cl : cr;
+  const int G = pick_chunks(2 * (size_t)cl * cr * d * std::max(wl, wr) * es, ce);
+  const int64_t cc = ce / G;
+  const size_t n1 = al256((size_t)(left ? cc * cr : cl * cc) * d * std::max(wl, wr) * es);
   TNB_TRY(ws_require(h, 2 * n1));
   void *t0, *t1;
   TNB_TRY(ws_alloc(h, n1, &t0));
   TNB_TRY(ws_alloc(h, n1, &t1));
+  double one[2] = {1.0, 0.0};
   // labels: l, l', a, s, r, s', b, r'
   enum { l = 0, lp, a, s, r, sp, b, rp };
-  if (left) {
-    {  // T1[l',a,s,r] = L[l,l',a] A[l,s,r]
-      int64_t ea[] = {cl, cl, wl}; int32_t ma[] = {l, lp, a};
-      int64_t eb[] = {cl, d, cr};  int32_t mb[] = {l, s, r};
-      int64_t ec[] = {cl, wl, d, cr}; int32_t mc[] = {lp, a, s, r};
-      TNB_TRY(contract_impl(h, dtype, 3, ea, ma, E, 3, eb, mb, A, 4, ec, mc, t0, nullptr, nullptr, 0, st));
-    }
-    {  // T2[l',r,s',b] = T1 W[a,s,s',b]
-      int64_t ea[] = {cl, wl, d, cr}; int32_t ma[] = {lp, a, s, r};
-      int64_t eb[] = {wl, d, d, wr};  int32_t mb[] = {a, s, sp, b};
-      int64_t ec[] = {cl, cr, d, wr}; int32_t mc[] = {lp, r, sp, b};
-      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t0, 4, eb, mb, W, 4, ec, mc, t1, nullptr, nullptr, 0, st));
-    }
-    {  // Lnew[r,r',b] = T2 conj(A)[l',s',r']
-      int64_t ea[] = {cl, cr, d, wr}; int32_t ma[] = {lp, r, sp, b};
-      int64_t eb[] = {cl, d, cr};     int32_t mb[] = {lp, sp, rp};
-      int64_t ec[] = {cr, cr, wr};    int32_t mc[] = {r, rp, b};
-      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t1, 3, eb, mb, A, 3, ec, mc, Enew, nullptr, nullptr, TNB_CONJ_B, st));
-    }
-  } else {
-    // here E = R[r,r',c] with c = right MPO bond (wr), A[l,s,r], W[a,s,s',c]; labels b == c
-    {  // T1[r',c,l,s] = R[r,r',c] A[l,s,r]
-      int64_t ea[] = {cr, cr, wr}; int32_t ma[] = {r, rp, b};
-      int64_t eb[] = {cl, d, cr};  int32_t mb[] = {l, s, r};
-      int64_t ec[] = {cr, wr, cl, d}; int32_t mc[] = {rp, b, l, s};
-      TNB_TRY(contract_impl(h, dtype, 3, ea, ma, E, 3, eb, mb, A, 4, ec, mc, t0, nullptr, nullptr, 0, st));
-    }
-    {  // T2[r',l,a,s'] = T1 W[a,s,s',c]
-      int64_t ea[] = {cr, wr, cl, d}; int32_t ma[] = {rp, b, l, s};
-      int64_t eb[] = {wl, d, d, wr};  int32_t mb[] = {a, s, sp, b};
-      int64_t ec[] = {cr, cl, wl, d}; int32_t mc[] = {rp, l, a, sp};
-      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t0, 4, eb, mb, W, 4, ec, mc, t1, nullptr, nullptr, 0, st));
-    }
-    {  // Rnew[l,l',a] = T2 conj(A)[l',s',r']
-      int64_t ea[] = {cr, cl, wl, d}; int32_t ma[] = {rp, l, a, sp};
-      int64_t eb[] = {cl, d, cr};     int32_t mb[] = {lp, sp, rp};
-      int64_t ec[] = {cl, cl, wl};    int32_t mc[] = {l, lp, a};
-      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t1, 3, eb, mb, A, 3, ec, mc, Enew, nullptr, nullptr, TNB_CONJ_B, st));
+  for (int j = 0; j < G; ++j) {
+    const void* beta = j ? one : nullptr;
+    if (left) {
+      {  // T1[l'_c,a,s,r] = L[l,l'_c,a] A[l,s,r]      (L window over l')
+        int64_t ea[] = {cl, cc, wl}; int32_t ma[] = {l, lp, a};
+        int64_t sa[] = {1, cl, cl * cl};
+        int64_t eb[] = {cl, d, cr};  int32_t mb[] = {l, s, r};
+        int64_t ec[] = {cc, wl, d, cr}; int32_t mc[] = {lp, a, s, r};
+        TNB_TRY(contract_impl_ex(h, dtype, 3, ea, ma, (const char*)E + (size_t)j * cc * cl * es, 3, eb, mb, A, 4, ec, mc, t0, nullptr,
+                                 nullptr, 0, st, nullptr, nullptr, 0, sa, nullptr));
+      }
+      {  // T2[l'_c,r,s',b] = T1 W[a,s,s',b]
+        int64_t ea[] = {cc, wl, d, cr}; int32_t ma[] = {lp, a, s, r};
+        int64_t eb[] = {wl, d, d, wr};  int32_t mb[] = {a, s, sp, b};
+        int64_t ec[] = {cc, cr, d, wr}; int32_t mc[] = {lp, r, sp, b};
+        TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t0, 4, eb, mb, W, 4, ec, mc, t1, nullptr, nullptr, 0, st));
+      }
+      {  // Lnew[r,r',b] (+)= T2 conj(A)[l'_c,s',r']   (A window over its first mode)
+        int64_t ea[] = {cc, cr, d, wr}; int32_t ma[] = {lp, r, sp, b};
+        int64_t eb[] = {cc, d, cr};     int32_t mb[] = {lp, sp, rp};
+        int64_t sb[] = {1, cl, cl * d};
+        int64_t ec[] = {cr, cr, wr};    int32_t mc[] = {r, rp, b};
+        TNB_TRY(contract_impl_ex(h, dtype, 4, ea, ma, t1, 3, eb, mb, (const char*)A + (size_t)j * cc * es, 3, ec, mc, Enew, nullptr,
+                                 beta, TNB_CONJ_B, st, nullptr, nullptr, 0, nullptr, sb));
+      }
+    } else {
+      // here E = R[r,r',c] with c = right MPO bond (wr), A[l,s,r], W[a,s,s',c]; labels b == c
+      {  // T1[r'_c,c,l,s] = R[r,r'_c,c] A[l,s,r]      (R window over r')
+        int64_t ea[] = {cr, cc, wr}; int32_t ma[] = {r, rp, b};
+        int64_t sa[] = {1, cr, cr * cr};
+        int64_t eb[] = {cl, d, cr};  int32_t mb[] = {l, s, r};
+        int64_t ec[] = {cc, wr, cl, d}; int32_t mc[] = {rp, b, l, s};
+        TNB_TRY(contract_impl_ex(h, dtype, 3, ea, ma, (const char*)E + (size_t)j * cc * cr * es, 3, eb, mb, A, 4, ec, mc, t0, nullptr,
+                                 nullptr, 0, st, nullptr, nullptr, 0, sa, nullptr));
+      }
+      {  // T2[r'_c,l,a,s'] = T1 W[a,s,s',c]
+        int64_t ea[] = {cc, wr, cl, d}; int32_t ma[] = {rp, b, l, s};
+        int64_t eb[] = {wl, d, d, wr};  int32_t mb[] = {a, s, sp, b};
+        int64_t ec[] = {cc, cl, wl, d}; int32_t mc[] = {rp, l, a, sp};
+        TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t0, 4, eb, mb, W, 4, ec, mc, t1, nullptr, nullptr, 0, st));
+      }
+      {  // Rnew[l,l',a] (+)= T2 conj(A)[l',s',r'_c]   (A slab over its last mode: contiguous)
+        int64_t ea[] = {cc, cl, wl, d}; int32_t ma[] = {rp, l, a, sp};
+        int64_t eb[] = {cl, d, cc};     int32_t mb[] = {lp, sp, rp};
+        int64_t ec[] = {cl, cl, wl};    int32_t mc[] = {l, lp, a};
+        TNB_TRY(contract_impl(h, dtype, 4, ea, ma, t1, 3, eb, mb, (const char*)A + (size_t)j * cc * cl * d * es, 3, ec, mc, Enew,
+                              nullptr, beta, TNB_CONJ_B, st));
+      }
     }
   }
   return TNB_OK;
@@ -487,7 +549,7 @@ int lanczos_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, co
         TNB_TRY(comm_barrier(h, st));
         w = ob[h->comm.rank];
       } else {
-        TNB_TRY(heff_core(h, dtype, d, d->chiL, L, W1, W2, R, V(j), w, t0, t1, st));
+        TNB_TRY(heff_apply_any(h, dtype, d, L, W1, W2, R, V(j), w, t0, t1, st));
       }
       ++nmv;
       // alpha_j = Re <v_j, w>
@@ -537,45 +599,59 @@ int noise_term_impl(Handle* h, int dtype, const tnb_bond_dims* d, const void* L,
                     const void* W2, const void* R, const void* phi, int ortho, double noise,
                     int accumulate, void* rho, void* t0, void* t1, cudaStream_t st) {
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
-  double alpha[2] = {noise, 0.0}, beta[2] = {accumulate ? 1.0 : 0.0, 0.0};
-  if (ortho == TNB_ORTHO_LEFT) {
-    {  // T1[s1,s2,r,l',a] = phi L          (re-ordered: (phi*L)*W1 instead of (L*W1)*phi)
-      int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
-      int64_t eb[] = {cl, cl, wl};     int32_t mb[] = {mL, mLp, mA};
-      int64_t ec[] = {d1, d2, cr, cl, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
-      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, L, 5, ec, mc, t0, nullptr, nullptr, 0, st));
-    }
-    {  // nt[s2,r,l',s1',b] = T1 W1
-      int64_t ea[] = {d1, d2, cr, cl, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
-      int64_t eb[] = {wl, d1, d1, wm};     int32_t mb[] = {mA, mS1, mS1p, mB};
-      int64_t ec[] = {d2, cr, cl, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
-      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W1, 5, ec, mc, t1, nullptr, nullptr, 0, st));
-    }
-    {  // rho[l',s1',l'',s1''] (+)= noise * nt conj(nt)
-      int64_t ea[] = {d2, cr, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
-      int32_t mb[] = {mS2, mR, mLpp, mS1pp, mB};
-      int64_t ec[] = {cl, d1, cl, d1};     int32_t mc[] = {mLp, mS1p, mLpp, mS1pp};
-      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B | TNB_HERM_UPPER, st));
-    }
-  } else {
-    {  // T1[l,s1,s2,r',c] = phi R
-      int64_t ea[] = {cl, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
-      int64_t eb[] = {cr, cr, wr};     int32_t mb[] = {mR, mRp, mC};
-      int64_t ec[] = {cl, d1, d2, cr, wr}; int32_t mc[] = {mL, mS1, mS2, mRp, mC};
-      TNB_TRY(contract_impl(h, dtype, 4, ea, ma, phi, 3, eb, mb, R, 5, ec, mc, t0, nullptr, nullptr, 0, st));
-    }
-    {  // nt[l,s1,s2',r',b] = T1 W2[b,s2,s2',c]   ((s2',r') in rho's own order, so that the Gram below may skip
-       //                                            its strictly-lower tiles)
-      int64_t ea[] = {cl, d1, d2, cr, wr}; int32_t ma[] = {mL, mS1, mS2, mRp, mC};
-      int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
-      int64_t ec[] = {cl, d1, d2, cr, wm}; int32_t mc[] = {mL, mS1, mS2p, mRp, mB};
-      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W2, 5, ec, mc, t1, nullptr, nullptr, 0, st));
-    }
-    {  // rho[s2',r',s2'',r''] (+)= noise * nt conj(nt)
-      int64_t ea[] = {cl, d1, d2, cr, wm}; int32_t ma[] = {mL, mS1, mS2p, mRp, mB};
-      int32_t mb[] = {mL, mS1, mS2pp, mRpp, mB};
-      int64_t ec[] = {d2, cr, d2, cr};     int32_t mc[] = {mS2p, mRp, mS2pp, mRpp};
-      TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B | TNB_HERM_UPPER, st));
+  const size_t es = elsize(dtype);
+  double alpha[2] = {noise, 0.0}, one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+  // t0 / t1 hold heff_workspace_bytes / 2 each: when H_eff is cut into G slabs, the noise term is cut into G chunks of
+  // an index the Gram product sums over (r for ortho left, l for ortho right) and accumulates with beta = 1
+  int G = heff_nchunks(dtype, d);
+  const int64_t ce = (ortho == TNB_ORTHO_LEFT) ? cr : cl;
+  while (G > 1 && ce % G) G /= 2;
+  if (G < heff_nchunks(dtype, d)) return set_err(h, TNB_ERR_UNSUPPORTED, "noise_term: cannot cut bond %lld into %d chunks", (long long)ce, heff_nchunks(dtype, d));
+  const int64_t cc = ce / G;
+  for (int j = 0; j < G; ++j) {
+    const void* beta = (j || accumulate) ? one : zero;
+    if (ortho == TNB_ORTHO_LEFT) {
+      {  // T1[s1,s2,r_c,l',a] = phi[l,s1,s2,r_c] L          (re-ordered: (phi*L)*W1 instead of (L*W1)*phi)
+        int64_t ea[] = {cl, d1, d2, cc}; int32_t ma[] = {mL, mS1, mS2, mR};
+        int64_t eb[] = {cl, cl, wl};     int32_t mb[] = {mL, mLp, mA};
+        int64_t ec[] = {d1, d2, cc, cl, wl}; int32_t mc[] = {mS1, mS2, mR, mLp, mA};
+        TNB_TRY(contract_impl(h, dtype, 4, ea, ma, (const char*)phi + (size_t)j * cc * cl * d1 * d2 * es, 3, eb, mb, L, 5, ec, mc, t0,
+                              nullptr, nullptr, 0, st));
+      }
+      {  // nt[s2,r_c,l',s1',b] = T1 W1
+        int64_t ea[] = {d1, d2, cc, cl, wl}; int32_t ma[] = {mS1, mS2, mR, mLp, mA};
+        int64_t eb[] = {wl, d1, d1, wm};     int32_t mb[] = {mA, mS1, mS1p, mB};
+        int64_t ec[] = {d2, cc, cl, d1, wm}; int32_t mc[] = {mS2, mR, mLp, mS1p, mB};
+        TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W1, 5, ec, mc, t1, nullptr, nullptr, 0, st));
+      }
+      {  // rho[l',s1',l'',s1''] (+)= noise * nt conj(nt)
+        int64_t ea[] = {d2, cc, cl, d1, wm}; int32_t ma[] = {mS2, mR, mLp, mS1p, mB};
+        int32_t mb[] = {mS2, mR, mLpp, mS1pp, mB};
+        int64_t ec[] = {cl, d1, cl, d1};     int32_t mc[] = {mLp, mS1p, mLpp, mS1pp};
+        TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B | TNB_HERM_UPPER, st));
+      }
+    } else {
+      {  // T1[l_c,s1,s2,r',c] = phi[l_c,s1,s2,r] R     (phi window over its first mode)
+        int64_t ea[] = {cc, d1, d2, cr}; int32_t ma[] = {mL, mS1, mS2, mR};
+        int64_t sa[] = {1, cl, cl * d1, cl * d1 * d2};
+        int64_t eb[] = {cr, cr, wr};     int32_t mb[] = {mR, mRp, mC};
+        int64_t ec[] = {cc, d1, d2, cr, wr}; int32_t mc[] = {mL, mS1, mS2, mRp, mC};
+        TNB_TRY(contract_impl_ex(h, dtype, 4, ea, ma, (const char*)phi + (size_t)j * cc * es, 3, eb, mb, R, 5, ec, mc, t0, nullptr,
+                                 nullptr, 0, st, nullptr, nullptr, 0, sa, nullptr));
+      }
+      {  // nt[l_c,s1,s2',r',b] = T1 W2[b,s2,s2',c]   ((s2',r') in rho's own order, so that the Gram below may skip
+         //                                              its strictly-lower tiles)
+        int64_t ea[] = {cc, d1, d2, cr, wr}; int32_t ma[] = {mL, mS1, mS2, mRp, mC};
+        int64_t eb[] = {wm, d2, d2, wr};     int32_t mb[] = {mB, mS2, mS2p, mC};
+        int64_t ec[] = {cc, d1, d2, cr, wm}; int32_t mc[] = {mL, mS1, mS2p, mRp, mB};
+        TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t0, 4, eb, mb, W2, 5, ec, mc, t1, nullptr, nullptr, 0, st));
+      }
+      {  // rho[s2',r',s2'',r''] (+)= noise * nt conj(nt)
+        int64_t ea[] = {cc, d1, d2, cr, wm}; int32_t ma[] = {mL, mS1, mS2p, mRp, mB};
+        int32_t mb[] = {mL, mS1, mS2pp, mRpp, mB};
+        int64_t ec[] = {d2, cr, d2, cr};     int32_t mc[] = {mS2p, mRp, mS2pp, mRpp};
+        TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 5, ea, mb, t1, 4, ec, mc, rho, alpha, beta, TNB_CONJ_B | TNB_HERM_UPPER, st));
+      }
     }
   }
   return TNB_OK;
@@ -593,10 +669,10 @@ static int heff_host_pipelined(Handle* h, int dtype, const tnb_bond_dims* d, con
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
   const size_t es = elsize(dtype);
   const size_t nb = (size_t)cl * cr * d1 * d2 * es;
-  const int NC = (cr >= 1024) ? 4 : 1;
+  const int NC = (cr >= 1024 && heff_nchunks(dtype, d) == 1) ? 4 : 1;
   if (NC == 1) {
     TNB_CUDA(h, cudaMemcpyAsync(dphi, phi_host, nb, cudaMemcpyHostToDevice, st));
-    TNB_TRY(heff_core(h, dtype, d, cl, L, W1, W2, R, dphi, dout, t0, t1, st));
+    TNB_TRY(heff_apply_any(h, dtype, d, L, W1, W2, R, dphi, dout, t0, t1, st));
     TNB_CUDA(h, cudaMemcpyAsync(out_host, dout, nb, cudaMemcpyDeviceToHost, st));
     return check_cuda(h, cudaStreamSynchronize(st), "heff_apply_host sync");
   }
@@ -664,8 +740,11 @@ static int heff_host_pipelined(Handle* h, int dtype, const tnb_bond_dims* d, con
 
 int heff_core_pub(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, const void* W1, const void* W2,
                   const void* R, const void* phi, void* out, void* t0, void* t1, cudaStream_t st) {
-  return heff_core(h, dtype, d, d->chiL, L, W1, W2, R, phi, out, t0, t1, st);
+  return heff_apply_any(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
 }
+
+void set_ws_limit(size_t bytes) { g_ws_limit = bytes ? bytes : ((size_t)40 << 30); }
+size_t get_ws_limit() { return g_ws_limit; }
 
 }  // namespace tnb
 
@@ -674,6 +753,17 @@ using namespace tnb;
 #define ST ((cudaStream_t)stream)
 
 extern "C" {
+
+int tnb_set_workspace_limit(tnb_handle_t h, size_t bytes) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  set_ws_limit(bytes);
+  return TNB_OK;
+}
+
+size_t tnb_get_workspace_limit(tnb_handle_t h) {
+  (void)h;
+  return get_ws_limit();
+}
 
 int tnb_heff_apply(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L, const void* W1,
                    const void* W2, const void* R, const void* phi, void* out, void* stream) {

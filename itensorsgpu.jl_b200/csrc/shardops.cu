@@ -313,7 +313,8 @@ int tnb_dmrg_bond_step_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* d, 
   sc.out[0] = out_a_peers;
   sc.out[1] = out_b_peers;
   const size_t hw_slab = heff_shard_ws_bytes(dtype, d, sc.clp);
-  const size_t hw_full = heff_workspace_bytes(dtype, d);
+  // the gathered noise tensor is full size whatever the single-GPU chunking of H_eff would be
+  const size_t hw_full = 2 * al256((size_t)cl * cr * d1 * d2 * std::max({d->wL, d->wM, d->wR}) * es);
   const size_t lan = hw_slab + (size_t)(krylovdim + 1) * phib + (1 << 16);
   const size_t nz = hw_slab / 2 + hw_full / 2 + (1 << 16);              // noise: slab-size T1 + full-size nt
   size_t need = phib + (noise > 0 ? al256((size_t)r * r * es) : 0);
