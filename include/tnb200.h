@@ -75,6 +75,15 @@ int tnb_version(void);
  * synchronises the device). */
 int tnb_reserve(tnb_handle_t h, size_t bytes);
 size_t tnb_workspace_bytes(tnb_handle_t h);
+/* Plan cache of tnb_contract -- the analogue of the reference's `ContractionPlans` dictionary and cuTENSOR autotune
+ * (src/ITensorsGPU.jl:54-55, src/tensor/cudense.jl:285-326).  Key: dtype, flags, (mode, extent, stride) of all three
+ * operands, base-pointer alignment; value: the grouped GEMM parameters and the kernel variant.  A hit skips planning.
+ * With autotune on (default) a NEW shape of at least 2e9 flop with beta = 0 is timed once with each tile configuration
+ * on the caller's operands (the first call of such a shape synchronises); every candidate sums each output element in
+ * the same k order, so the choice never changes a bit of the result.  mode: 0 = heuristic only, 1 = autotune. */
+int tnb_plan_cache_stats(tnb_handle_t h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* autotuned);
+int tnb_plan_cache_clear(tnb_handle_t h);
+int tnb_set_autotune(tnb_handle_t h, int mode);
 /* Upper bound (bytes) on the PAIR of temporaries of one H_eff*phi / noise term / environment update (default 40 GB;
  * 0 restores the default).  Above it the work is cut into slabs of the output bond (H_eff: independent
  * full-efficiency slabs, L taken as a strided window, result written as a strided window) or of a summed bond with

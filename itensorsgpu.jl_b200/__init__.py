@@ -7,10 +7,11 @@ ITensor-level interface: ``cu``, ``cpu``, ``*``, ``+``, ``svd``, ``eigen``, ``qr
 ``apply``).  The directory name is not an importable identifier; import it through the
 repo-root shim:  ``from itensorsgpu_b200 import tn``.
 """
-from . import _lib, ops, itensor, mps, shard, tebd  # noqa: F401
+from . import _lib, ops, itensor, mps, shard, tebd, io  # noqa: F401
 from ._lib import TnbError, DimensionMismatch, handle, load  # noqa: F401
 from .ops import DTensor  # noqa: F401
 from .itensor import (Index, ITensor, cu, cpu, cuITensor, randomCuITensor, prime, dag, noprime, norm, dot, permute,  # noqa: F401
-                      svd, eigen, qr, davidson, commonind, delta)
-from .mps import (MPS, MPO, Sweeps, dmrg, apply, inner, orthogonalize, add, truncate, contract, cuMPS, cuMPO, randomCuMPS, productCuMPS,  # noqa: F401
+                      svd, eigen, qr, davidson, commonind, delta, diagITensor)
+from .mps import (MPS, MPO, Sweeps, dmrg, apply, inner, orthogonalize, add, truncate, contract, contract_mpo, add_mpo, truncate_mpo, cuMPS, cuMPO, randomCuMPS, productCuMPS,  # noqa: F401
                   randomCuMPO, heisenberg_mpo, tfim_mpo)
+from .io import save_chain, load_chain, save_itensor, load_itensor  # noqa: F401

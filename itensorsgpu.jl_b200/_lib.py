@@ -47,6 +47,9 @@ SIGNATURES = {
     "tnb_reserve": (_int, [_vp, C.c_size_t]),
     "tnb_workspace_bytes": (C.c_size_t, [_vp]),
     "tnb_launch_count": (C.c_uint64, [_vp]),
+    "tnb_plan_cache_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tnb_plan_cache_clear": (_int, [_vp]),
+    "tnb_set_autotune": (_int, [_vp, _int]),
     "tnb_set_workspace_limit": (_int, [_vp, C.c_size_t]),
     "tnb_get_workspace_limit": (C.c_size_t, [_vp]),
     "tnb_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp,
@@ -142,6 +145,18 @@ class Handle:
     @property
     def launches(self):
         return int(self.lib.tnb_launch_count(self.h))
+
+    def plan_cache_stats(self):
+        """{'entries', 'hits', 'misses', 'autotuned'} of the contraction plan cache (``ContractionPlans`` analogue)"""
+        v = [C.c_uint64(0) for _ in range(4)]
+        self.check(self.lib.tnb_plan_cache_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("entries", "hits", "misses", "autotuned"), [int(x.value) for x in v]))
+
+    def plan_cache_clear(self):
+        self.check(self.lib.tnb_plan_cache_clear(self.h))
+
+    def set_autotune(self, on):
+        self.check(self.lib.tnb_set_autotune(self.h, 1 if on else 0))
 
     def set_workspace_limit(self, nbytes):
         """bound on the pair of temporaries of one matvec / noise term / environment update (0 = default 40 GB)"""

@@ -5,6 +5,12 @@
 
 namespace tnb {
 
+// plan cache of the contraction engine (contract.cu)
+void plan_cache_drop(Handle* h);
+void plan_cache_clear(Handle* h);
+void plan_cache_stats(Handle* h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* tuned);
+void plan_cache_set_autotune(Handle* h, int mode);
+
 int set_err(Handle* h, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -109,6 +115,7 @@ int tnb_destroy(tnb_handle_t h) {
   if (H->scal_host) cudaFreeHost(H->scal_host);
   for (auto& e : H->ev) if (e) cudaEventDestroy(e);
   if (H->copy_stream) cudaStreamDestroy(H->copy_stream);
+  plan_cache_drop(H);
   delete H;
   return TNB_OK;
 }
@@ -122,6 +129,25 @@ int tnb_reserve(tnb_handle_t h, size_t bytes) {
 }
 
 size_t tnb_workspace_bytes(tnb_handle_t h) { return h ? H->ws_bytes : 0; }
+int tnb_plan_cache_stats(tnb_handle_t h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* autotuned) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  plan_cache_stats(H, entries, hits, misses, autotuned);
+  return TNB_OK;
+}
+
+int tnb_plan_cache_clear(tnb_handle_t h) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  plan_cache_clear(H);
+  return TNB_OK;
+}
+
+int tnb_set_autotune(tnb_handle_t h, int mode) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (mode != 0 && mode != 1) return set_err(H, TNB_ERR_BAD_ARG, "set_autotune: mode %d", mode);
+  plan_cache_set_autotune(H, mode);
+  return TNB_OK;
+}
+
 uint64_t tnb_launch_count(tnb_handle_t h) { return h ? H->launches : 0; }
 
 int tnb_contract(tnb_handle_t h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,

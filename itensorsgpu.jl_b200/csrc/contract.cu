@@ -18,6 +18,9 @@
 #include <array>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 
 namespace tnb {
 
@@ -27,28 +30,88 @@ int launch_tiles_c128(Handle* h, GemmParams& p, bool ak, bool bk, int va, int vb
 int launch_smallk_f64(Handle* h, GemmParams& p, cudaStream_t st);
 int launch_smallk_c128(Handle* h, GemmParams& p, cudaStream_t st);
 
+// ------------------------------------------------------------------------------------
+// Plan cache (the analogue of the reference's `ContractionPlans` dictionary + cuTENSOR autotune,
+// /root/reference/src/ITensorsGPU.jl:54-55 and src/tensor/cudense.jl:285-326, which keys a string of (mode, extent)
+// pairs).  Key: dtype, flags, every (mode label, extent, stride) of the three operands and the 16-byte alignment of
+// the base pointers.  Value: the grouped / merged GEMM parameters and the kernel variant (staging directions, copy
+// widths, tile configuration).  A hit skips the whole planning step (mode matching, grouping, merging -- what
+// dominates the host time of the small contractions of C1); a miss plans once and, when autotuning is on and the
+// call is idempotent (beta = 0), times the candidate tile configurations on the caller's own operands and keeps the
+// fastest.  All candidates accumulate every output element in the same k order, so the choice never changes a bit of
+// the result (ranks of a sharded sweep stay bit-identical whatever each one measured).
+// ------------------------------------------------------------------------------------
+struct Variant {
+  bool smallk = false;
+  bool ak = true, bk = true;
+  int va = 1, vb = 1;
+  bool small = false;
+};
+struct Plan {
+  GemmParams p;
+  Variant v;
+  bool tuned = false;
+};
+struct PlanCache {
+  std::unordered_map<std::string, Plan> map;
+  uint64_t hits = 0, misses = 0, tuned = 0;
+  int autotune = 1;                 // 0: heuristic only, 1: time the tile configurations of new large shapes
+};
+static std::unordered_map<Handle*, PlanCache>& caches() {
+  static std::unordered_map<Handle*, PlanCache> c;
+  return c;
+}
+static std::mutex& cache_mutex() { static std::mutex m; return m; }
+
+void plan_cache_drop(Handle* h) {
+  std::lock_guard<std::mutex> g(cache_mutex());
+  caches().erase(h);
+}
+void plan_cache_stats(Handle* h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* tuned) {
+  std::lock_guard<std::mutex> g(cache_mutex());
+  PlanCache& c = caches()[h];
+  if (entries) *entries = c.map.size();
+  if (hits) *hits = c.hits;
+  if (misses) *misses = c.misses;
+  if (tuned) *tuned = c.tuned;
+}
+void plan_cache_set_autotune(Handle* h, int mode) {
+  std::lock_guard<std::mutex> g(cache_mutex());
+  caches()[h].autotune = mode;
+}
+void plan_cache_clear(Handle* h) {
+  std::lock_guard<std::mutex> g(cache_mutex());
+  PlanCache& c = caches()[h];
+  c.map.clear();
+  c.hits = c.misses = c.tuned = 0;
+}
+
 static bool all_even(const long long* s, int from, int n) {
   for (int i = from; i < n; ++i)
     if (s[i] & 1) return false;
   return true;
 }
 
-// Decide per-operand staging direction and copy width, pick a tile config, launch.
-static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) {
+static void set_scalars(GemmParams& p, int dtype, const void* alpha, const void* beta);
+
+// Decide per-operand staging direction and copy width and pick a tile config (heuristic).
+static Variant choose_variant(Handle* h, int dtype, const GemmParams& p) {
+  Variant v;
   const bool cplx = dtype == TNB_C128;
   {  // small-K / small-N streaming form
     static const bool off = getenv("TNB_SMALLK") && !strcmp(getenv("TNB_SMALLK"), "off");
     if (!off && p.K <= 32 && p.N <= 32 && p.M >= 16384 && p.batch <= 1 && !p.boffA && !p.boffB && !p.boffC && !p.splitN &&
-        p.npeer == 0 && !p.lowerOnly)
-      return cplx ? launch_smallk_c128(h, p, st) : launch_smallk_f64(h, p, st);
+        p.npeer == 0 && !p.lowerOnly) {
+      v.smallk = true;
+      return v;
+    }
   }
   // A: contiguous along K if the first K mode has unit stride in A; along M if the first M mode has.
-  bool ak, bk;
   int va = 1, vb = 1;
   const bool a_k1 = p.gk.sX[0] == 1 && p.K > 1, a_m1 = p.gm.sX[0] == 1 && p.M > 1;
   const bool b_k1 = p.gk.sY[0] == 1 && p.K > 1, b_n1 = p.gn.sX[0] == 1 && p.N > 1;
-  ak = a_k1 || !a_m1;
-  bk = b_k1 || !b_n1;
+  v.ak = a_k1 || !a_m1;
+  v.bk = b_k1 || !b_n1;
   if (!cplx) {
     if (a_k1) {
       if ((p.gk.ext[0] % 2 == 0) && all_even(p.gk.sX, 1, p.gk.n) && all_even(p.gm.sX, 0, p.gm.n) &&
@@ -67,15 +130,62 @@ static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) 
   }
   if (!p.boffA && (p.bstrideA & 1)) va = 1;   // batched: 16-byte copies need even element offsets
   if (!p.boffB && (p.bstrideB & 1)) vb = 1;   // (offset tables must hold even offsets for f64)
+  v.va = va; v.vb = vb;
   // tile config: big tiles unless they cannot fill the machine (tile shapes: contract_kernel.cuh -- real 64x128
   // / 64x64, complex 64x64 / 64x32)
   auto ntiles = [&](int bm, int bn) { return ((long long)(p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * std::max(p.batch, 1); };
-  if (!cplx) {
-    const bool small = ntiles(64, 128) < h->num_sms || p.M <= 64 || p.N <= 64;
-    return launch_tiles_f64(h, p, ak, bk, va, vb, small, st);
+  if (!cplx) v.small = ntiles(64, 128) < h->num_sms || p.M <= 64 || p.N <= 64;
+  else v.small = ntiles(64, 64) < h->num_sms || p.M <= 64 || p.N <= 32;
+  return v;
+}
+
+static int launch_variant(Handle* h, int dtype, GemmParams& p, const Variant& v, cudaStream_t st) {
+  const bool cplx = dtype == TNB_C128;
+  if (v.smallk) return cplx ? launch_smallk_c128(h, p, st) : launch_smallk_f64(h, p, st);
+  if (!cplx) return launch_tiles_f64(h, p, v.ak, v.bk, v.va, v.vb, v.small, st);
+  return launch_tiles_c128(h, p, v.ak, v.bk, v.va, v.vb, v.small, st);
+}
+
+static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) {
+  const Variant v = choose_variant(h, dtype, p);
+  return launch_variant(h, dtype, p, v, st);
+}
+
+// One-shot autotune of a new shape: time the two tile configurations on the caller's operands (beta = 0 only: the
+// call is then idempotent) and keep the faster.  Returns with C holding the result.
+static int autotune_variant(Handle* h, int dtype, GemmParams& p, Variant& v, bool* tuned, cudaStream_t st) {
+  *tuned = false;
+  const double flop = 2.0 * p.M * (double)p.N * p.K * std::max(p.batch, 1) * (dtype == TNB_C128 ? 4 : 1);
+  const bool idempotent = p.beta_re == 0.0 && p.beta_im == 0.0;
+  // candidates differ only when both tile shapes are sensible: enough tiles for the small one to matter, and not so
+  // many that quantisation is irrelevant (> 8 waves of the big tile: keep the big tile)
+  const long long big_tiles = ((long long)(p.M + 63) / 64) * ((p.N + (dtype == TNB_C128 ? 63 : 127)) / (dtype == TNB_C128 ? 64 : 128)) * std::max(p.batch, 1);
+  if (v.smallk || !idempotent || flop < 2e9 || big_tiles > 8LL * 2 * h->num_sms || p.M <= 64 || p.N <= 64 || p.npeer > 0)
+    return launch_variant(h, dtype, p, v, st);
+  cudaEvent_t e[3];
+  for (auto& x : e) TNB_CUDA(h, cudaEventCreate(&x));
+  float best = 1e30f;
+  int rc = TNB_OK;
+  Variant bestv = v;
+  for (int cand = 0; cand < 2 && !rc; ++cand) {
+    Variant c = v;
+    c.small = cand == 1;
+    rc = launch_variant(h, dtype, p, c, st);                 // warm (instruction cache, L2)
+    if (rc) break;
+    cudaEventRecord(e[0], st);
+    rc = launch_variant(h, dtype, p, c, st);
+    cudaEventRecord(e[1], st);
+    if (rc) break;
+    cudaEventSynchronize(e[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e[0], e[1]);
+    if (ms < best) { best = ms; bestv = c; }
   }
-  const bool small = ntiles(64, 64) < h->num_sms || p.M <= 64 || p.N <= 32;
-  return launch_tiles_c128(h, p, ak, bk, va, vb, small, st);
+  for (auto& x : e) cudaEventDestroy(x);
+  if (rc) return rc;
+  v = bestv;
+  *tuned = true;
+  return TNB_OK;      // the last candidate run left a complete, correct C (every candidate computes the same bits)
 }
 
 // ------------------------------------------------------------------------------------
@@ -140,6 +250,31 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
   if (nA < 0 || nB < 0 || nC < 0 || nA > 64 || nB > 64 || nC > 64)
     return set_err(h, TNB_ERR_BAD_ARG, "contract: bad rank");
   if (!A || !B || !C) return set_err(h, TNB_ERR_BAD_ARG, "contract: null tensor pointer");
+  // ---- plan cache lookup
+  std::string key;
+  key.reserve(64 + 20 * (nA + nB + nC));
+  auto put = [&](long long x) { key.append((const char*)&x, sizeof(x)); };
+  put(dtype); put(flags & (TNB_CONJ_A | TNB_CONJ_B | TNB_HERM_UPPER)); put(nA); put(nB); put(nC); put(npeer);
+  put(((uintptr_t)A % 16 == 0) | (((uintptr_t)B % 16 == 0) << 1));
+  for (int i = 0; i < nA; ++i) { put(modeA[i]); put(extA[i]); put(strideA ? strideA[i] : -1); }
+  for (int i = 0; i < nB; ++i) { put(modeB[i]); put(extB[i]); put(strideB ? strideB[i] : -1); }
+  for (int i = 0; i < nC; ++i) { put(modeC[i]); put(extC[i]); put(strideC ? strideC[i] : -1); }
+  PlanCache* cache;
+  {
+    std::lock_guard<std::mutex> g(cache_mutex());
+    cache = &caches()[h];
+  }
+  {
+    auto it = cache->map.find(key);
+    if (it != cache->map.end()) {
+      cache->hits++;
+      GemmParams p = it->second.p;
+      p.A = A; p.B = B; p.C = C;
+      set_scalars(p, dtype, alpha, beta);
+      for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
+      return launch_variant(h, dtype, p, it->second.v, st);
+    }
+  }
   std::vector<ModeRec> recs;
   auto find = [&](int label) -> ModeRec* {
     for (auto& r : recs) if (r.label == label) return &r;
@@ -224,7 +359,19 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
   }
   p.npeer = npeer;
   for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
-  return launch_planned(h, dtype, p, st);
+  cache->misses++;
+  Plan plan;
+  plan.v = choose_variant(h, dtype, p);
+  int rc;
+  if (cache->autotune) rc = autotune_variant(h, dtype, p, plan.v, &plan.tuned, st);
+  else rc = launch_variant(h, dtype, p, plan.v, st);
+  if (rc) return rc;
+  if (plan.tuned) cache->tuned++;
+  plan.p = p;
+  plan.p.A = plan.p.B = nullptr; plan.p.C = nullptr;
+  if (cache->map.size() > 65536) cache->map.clear();        // unbounded shape churn: start over
+  cache->map.emplace(std::move(key), plan);
+  return TNB_OK;
 }
 
 int gemm_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64_t n, int64_t k,

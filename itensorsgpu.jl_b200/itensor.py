@@ -80,14 +80,34 @@ class DiagStore:
         return DTensor(torch.diag(self.vec).reshape(-1).contiguous(), (k, k))
 
 
+class UniformDiagStore:
+    """Uniform diagonal storage ([EXT] NDTensors ``Diag(x::Number)``: every diagonal entry equals ``value``; the
+    reference's ``UniformDiagTensor`` cases, ``src/tensor/cudiag.jl:105-133``).  Holds no device memory."""
+
+    def __init__(self, value, k):
+        self.value = complex(value) if isinstance(value, complex) and value.imag != 0 else float(np.real(value))
+        self.k = int(k)
+
+    @property
+    def dtype(self):
+        return torch.complex128 if isinstance(self.value, complex) else torch.float64
+
+    def dense(self):
+        return DTensor(torch.diag(torch.full((self.k,), self.value, dtype=self.dtype, device="cuda")).reshape(-1).contiguous(),
+                       (self.k, self.k))
+
+
 class ITensor:
-    """ITensor.  ``store`` is a DTensor (GPU dense, ``CuDense``), a DiagStore (GPU diagonal) or a NumPy array
-    (CPU container)."""
+    """ITensor.  ``store`` is a DTensor (GPU dense, ``CuDense``), a DiagStore (GPU diagonal), a UniformDiagStore
+    or a NumPy array (CPU container)."""
 
     def __init__(self, store, inds):
         self.inds = tuple(inds)
         dims = tuple(i.dim for i in self.inds)
-        if isinstance(store, DiagStore):
+        if isinstance(store, UniformDiagStore):
+            if len(dims) != 2 or dims[0] != dims[1] or dims[0] != store.k:
+                raise _lib.DimensionMismatch(2, "uniform Diag storage of length %d for indices of dims %s" % (store.k, dims))
+        elif isinstance(store, DiagStore):
             if len(dims) != 2 or dims[0] != dims[1] or dims[0] != store.vec.numel():
                 raise _lib.DimensionMismatch(2, "Diag storage of length %d for indices of dims %s" % (store.vec.numel(), dims))
         elif isinstance(store, DTensor):
@@ -102,11 +122,15 @@ class ITensor:
     # ---- placement
     @property
     def on_gpu(self):
-        return isinstance(self.store, (DTensor, DiagStore))
+        return isinstance(self.store, (DTensor, DiagStore, UniformDiagStore))
 
     @property
     def is_diag(self):
-        return isinstance(self.store, DiagStore)
+        return isinstance(self.store, (DiagStore, UniformDiagStore))
+
+    @property
+    def is_uniform_diag(self):
+        return isinstance(self.store, UniformDiagStore)
 
     def _dev(self):
         if not self.on_gpu:
@@ -115,6 +139,8 @@ class ITensor:
 
     def array(self):
         """Logical ndarray on the host (``array(cpu(A))``)."""
+        if self.is_uniform_diag:
+            return np.eye(self.store.k) * self.store.value
         if self.is_diag:
             return np.diag(self.store.vec.cpu().numpy())
         return self.store.numpy() if self.on_gpu else np.array(self.store)
@@ -137,6 +163,8 @@ class ITensor:
         return ITensor(self.store, [m.get(i, i) for i in self.inds])
 
     def dag(self):
+        if self.is_uniform_diag:
+            return ITensor(UniformDiagStore(np.conj(self.store.value), self.store.k), self.inds)
         if self.is_diag:
             return ITensor(DiagStore(torch.conj_physical(self.store.vec)), self.inds)
         s = self._dev()
@@ -157,11 +185,57 @@ class ITensor:
         C = ops.diag_contract(o.store, o.inds, shared, self.store.vec, lc)
         return ITensor(C, out_inds)
 
+    def _uniform_times_dense(self, o, diag_first):
+        """self: UniformDiag (u, v); o: dense sharing exactly one of u, v: a scale fused into the (possibly identity)
+        permutation to the NDTensors output order -- ONE pass (``cudiag.jl:105-118`` multiplies in place and ignores
+        the order, which is why ``Aij*scal`` is @test_broken at ``test/test_cudiag.jl:49,95``; here both orders hold)."""
+        u, v = self.inds
+        shared = u if u in o.inds else v
+        other = v if shared == u else u
+        free = [i for i in o.inds if i != shared]
+        out_inds = ([other] + free) if diag_first else (free + [other])
+        lc = [shared if i == other else i for i in out_inds]
+        src = o.store
+        val = self.store.value
+        if isinstance(val, complex) and src.dtype != torch.complex128:
+            src = src.astype(torch.complex128)
+        out = DTensor.empty(tuple(i.dim for i in out_inds), src.dtype, src.data.device)
+        ops.permute_axpby(src, o.inds, out, lc, alpha=val, beta=0.0)
+        return ITensor(out, out_inds)
+
+    def _diag_times_diag(self, o):
+        """Diag x Diag sharing exactly one index -> Diag over the two remaining indices: an elementwise product of the
+        two diagonals (``cudiag.jl:120-145``), or a scale when one of them is uniform."""
+        shared = [i for i in self.inds if i in o.inds][0]
+        a = [i for i in self.inds if i != shared][0]
+        b = [i for i in o.inds if i != shared][0]
+        if self.is_uniform_diag and o.is_uniform_diag:
+            return ITensor(UniformDiagStore(self.store.value * o.store.value, self.store.k), (a, b))
+        if self.is_uniform_diag or o.is_uniform_diag:
+            un, dg = (self, o) if self.is_uniform_diag else (o, self)
+            vec = dg.store.vec.clone()
+            if isinstance(un.store.value, complex) and vec.dtype != torch.complex128:
+                vec = vec.to(torch.complex128)
+            ops.scale(DTensor(vec, (vec.numel(),)), un.store.value)
+            return ITensor(DiagStore(vec), (a, b))
+        x, y = self.store.vec, o.store.vec
+        if x.dtype != y.dtype:
+            x, y = x.to(torch.complex128), y.to(torch.complex128)
+        if y.dtype == torch.complex128 or x.dtype == torch.float64:
+            out = ops.diag_contract(DTensor(x.contiguous(), (x.numel(),)), ("k",), "k", y, ("k",))
+        else:
+            out = ops.diag_contract(DTensor(y.contiguous(), (y.numel(),)), ("k",), "k", x, ("k",))
+        return ITensor(DiagStore(out.data), (a, b))
+
     def __mul__(self, o):
         if isinstance(o, ITensor):
+            if self.on_gpu and o.on_gpu and self.is_diag and o.is_diag and sum(i in o.inds for i in self.inds) == 1:
+                return self._diag_times_diag(o)
             if self.on_gpu and o.on_gpu and (self.is_diag != o.is_diag):            # cudiag.jl:105-161 without densifying
                 dg, dn = (self, o) if self.is_diag else (o, self)
                 if sum(i in dn.inds for i in dg.inds) == 1:
+                    if dg.is_uniform_diag:
+                        return dg._uniform_times_dense(dn, diag_first=self.is_diag)
                     return dg._diag_times_dense(dn, diag_first=self.is_diag)
             C, lc = ops.contract(self._dev(), self.inds, o._dev(), o.inds)        # contract!! (cudense.jl:83-110)
             return ITensor(C, lc)
@@ -229,6 +303,18 @@ def commonind(A, B):
 
 def delta(i, j, dtype=np.float64):
     return cuITensor(np.eye(i.dim, j.dim, dtype=dtype), (i, j))
+
+
+def diagITensor(x, i, j):
+    """``itensor(tensor(Diag(x), IndexSet(i, j)))`` (``test/test_cudiag.jl:30-44``): a vector gives (non-uniform) Diag
+    storage on the GPU, a number gives uniform Diag storage."""
+    if np.isscalar(x):
+        if i.dim != j.dim:
+            raise _lib.DimensionMismatch(2, "diagITensor: indices of dims %d, %d" % (i.dim, j.dim))
+        return ITensor(UniformDiagStore(x, i.dim), (i, j))
+    v = np.asarray(x)
+    v = v.astype(np.complex128 if np.iscomplexobj(v) else np.float64)
+    return ITensor(DiagStore(torch.from_numpy(np.ascontiguousarray(v)).cuda()), (i, j))
 
 
 # ---- constructors / transfer (src/cuitensor.jl)

@@ -114,10 +114,13 @@ def randomCuMPS(N, d, chi=1, seed=None, dtype=np.float64):
     return MPS(ts, llim=-1, rlim=1).cu()
 
 
-def randomCuMPO(N, d, seed=None):
-    """``randomCuMPO(sites)`` (``src/mps/cumpo.jl:15-23``): link dimension 1 only, like the reference."""
+def randomCuMPO(N, d, seed=None, linkdim=1):
+    """``randomCuMPO(sites)`` (``src/mps/cumpo.jl:15-23``: link dimension 1 only, where anything else is an
+    ArgumentError, ``:21``; ``linkdim`` generalises it)."""
+    if linkdim < 1:
+        raise _lib.TnbError(1, "randomCuMPO: link dimension must be >= 1")
     rng = np.random.default_rng(seed)
-    return MPO([rng.standard_normal((1, d, d, 1)) for _ in range(N)]).cu()
+    return MPO([rng.standard_normal((1 if j == 0 else linkdim, d, d, 1 if j == N - 1 else linkdim)) for j in range(N)]).cu()
 
 
 # ---- measurements
@@ -177,7 +180,10 @@ def orthogonalize(psi, j):
 # ---- MPS / MPO algebra on the same kernels ([EXT] ITensors `+`, `truncate!`, `contract(::MPO, ::MPS)`;
 #      the reference exercises them in test/test_cumpo.jl:42-173 and test/test_cumps.jl:196-246)
 def add(psi, phi):
-    """|psi> + |phi>: direct sum of the bond spaces (exact; follow with ``truncate``).  Block placement only."""
+    """|psi> + |phi>: direct sum of the bond spaces (exact; follow with ``truncate``).  Block placement only.
+    ``add(K::MPO, L::MPO)`` dispatches to ``add_mpo``."""
+    if isinstance(psi, MPO) and isinstance(phi, MPO):
+        return add_mpo(psi, phi)
     if not (psi.on_gpu and phi.on_gpu):
         raise _lib.TnbError(3, "add: move both MPS to the GPU with cu(); there is no CPU path")
     N = len(psi)
@@ -222,9 +228,60 @@ def truncate(psi, maxdim=None, cutoff=None):
     return MPS(ts, llim=-1, rlim=1)
 
 
+def _mpo_as_mps(H):
+    """MPO site W[a,s,s',b] viewed as an MPS site [a,(s,s'),b] (same buffer) -- what [EXT] truncate!(::MPO) works on"""
+    return MPS([DTensor(W.data, (W.dims[0], W.dims[1] * W.dims[2], W.dims[3])) for W in H.tensors]), \
+        [(W.dims[1], W.dims[2]) for W in H.tensors]
+
+
+def truncate_mpo(H, maxdim=None, cutoff=None):
+    """[EXT] ``truncate!(::MPO; maxdim, cutoff)``: the MPS algorithm on the fused site index (s, s')."""
+    if not H.on_gpu:
+        raise _lib.TnbError(3, "truncate_mpo: move H to the GPU with cu(); there is no CPU path")
+    psi, sd = _mpo_as_mps(H)
+    out = truncate(psi, maxdim=maxdim, cutoff=cutoff)
+    return MPO([DTensor(t.data, (t.dims[0], d1, d2, t.dims[2])) for t, (d1, d2) in zip(out.tensors, sd)])
+
+
+def contract_mpo(K, L, maxdim=None, cutoff=None):
+    """[EXT] ``contract(K::MPO, L::MPO; maxdim, cutoff)`` = the operator product K*L (L acts first) as an MPO
+    (``test/test_cumpo.jl:145-173``): site-wise product
+    M[(aL aK), s, s'', (bL bK)] = sum_{s'} L[aL,s,s',bL] K[aK,s',s'',bK] (one contraction per site), then truncation."""
+    if not (K.on_gpu and L.on_gpu):
+        raise _lib.TnbError(3, "contract: move both MPOs to the GPU with cu(); there is no CPU path")
+    if len(K) != len(L):
+        raise _lib.DimensionMismatch(2, "contract: MPOs of different length (%d, %d)" % (len(K), len(L)))
+    out = []
+    for j, (Wk, Wl) in enumerate(zip(K.tensors, L.tensors)):
+        if Wl.dims[2] != Wk.dims[1]:
+            raise _lib.DimensionMismatch(2, "contract: site dimensions differ at site %d" % j)
+        T, _ = ops.contract(Wl, ("al", "s", "t", "bl"), Wk, ("ak", "t", "u", "bk"), lc=("al", "ak", "s", "u", "bl", "bk"))
+        al, ak, sdim, u, bl, bk = T.dims
+        out.append(DTensor(T.data, (al * ak, sdim, u, bl * bk)))
+    res = MPO(out)
+    if maxdim is None and cutoff is None:
+        return res
+    return truncate_mpo(res, maxdim=maxdim, cutoff=cutoff)
+
+
+def add_mpo(K, L):
+    """[EXT] ``add(K::MPO, L::MPO)`` (``test/test_cumpo.jl:133-143``): direct sum of the bond spaces."""
+    if not (K.on_gpu and L.on_gpu):
+        raise _lib.TnbError(3, "add: move both MPOs to the GPU with cu(); there is no CPU path")
+    a, sd = _mpo_as_mps(K)
+    b, sd2 = _mpo_as_mps(L)
+    if sd != sd2:
+        raise _lib.DimensionMismatch(2, "add: site dimensions of the two MPOs differ")
+    out = add(a, b)
+    return MPO([DTensor(t.data, (t.dims[0], d1, d2, t.dims[2])) for t, (d1, d2) in zip(out.tensors, sd)])
+
+
 def contract(H, psi, maxdim=None, cutoff=None):
     """[EXT] ``contract(H::MPO, psi::MPS; maxdim, cutoff)`` = H|psi> as an MPS: site-wise product
-    B[(l a), s', (r b)] = sum_s W[a,s,s',b] A[l,s,r] (one contraction per site), then ``truncate``."""
+    B[(l a), s', (r b)] = sum_s W[a,s,s',b] A[l,s,r] (one contraction per site), then ``truncate``.
+    ``contract(K::MPO, L::MPO)`` dispatches to ``contract_mpo``."""
+    if isinstance(psi, MPO):
+        return contract_mpo(H, psi, maxdim=maxdim, cutoff=cutoff)
     if not (H.on_gpu and psi.on_gpu):
         raise _lib.TnbError(3, "contract: move H and psi to the GPU with cu(); there is no CPU path")
     if len(H) != len(psi):
@@ -321,7 +378,7 @@ class _EnvCache:
 
 
 def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None, env_store="device",
-         comm=None, shard_min_chi=256, verify_ranks=False):
+         comm=None, shard_min_chi=256, verify_ranks=False, checkpoint=None):
     """``energy, psi = dmrg(H, psi0, sweeps)`` ([EXT] ITensors 0.2 two-site DMRG; reference call sites
     ``examples/dmrg.jl:25``, ``test/dmrg.jl:27,75``).  Per bond: ONE fused C call (phi = A1*A2, Lanczos with
     krylovdim matvecs, optional noise term, truncated factorization) plus one environment update.
@@ -332,7 +389,11 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
     is divisible by the number of ranks and >= ``shard_min_chi`` are sharded over the output bond (``shard.ShardedSweep``);
     the factorization is replicated.  Energies and the MPS are bit-identical on every rank and equal to the 1-GPU
     sweep's up to the summation order of the sharded GEMMs (tests: 1e-12).  ``verify_ranks`` cross-checks
-    (energy, n_keep) over the ranks after every bond."""
+    (energy, n_keep) over the ranks after every bond.
+
+    ``checkpoint`` (a path): after every sweep the MPS (orthogonality centre back at site 0) is written with
+    ``io.save_chain`` together with {"sweeps_done", "energy"}; ``load_chain`` + ``dmrg`` with the remaining sweeps
+    resumes bit-identically (rank 0 writes when sharded)."""
     if not (H.on_gpu and psi0.on_gpu):
         raise _lib.TnbError(3, "dmrg: move H and psi0 to the GPU with cu(); there is no CPU path")
     N = len(psi0)
@@ -404,6 +465,9 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
         if outputlevel > 0:
             print("After sweep %d energy=%.12f maxlinkdim=%d maxerr=%.2E" %
                   (sw + 1, energy, max(t.dims[2] for t in ts[:-1]), maxerr))
+        if checkpoint and (comm is None or comm.rank == 0):
+            from .io import save_chain
+            save_chain(checkpoint, MPS(ts, llim=-1, rlim=1), extra={"sweeps_done": sw + 1, "energy": energy})
     out = MPS(ts, llim=-1, rlim=1)
     if sh is not None:
         out.shard_stats = {"sharded_bond_steps": sh.sharded_steps, "replicated_bond_steps": sh.replicated_steps}

@@ -154,3 +154,39 @@ def contract_mpo_mps(Ws, psi, maxdim=None, cutoff=None):
     if maxdim is None and cutoff is None:
         return out
     return truncate(out, maxdim=maxdim, cutoff=cutoff)
+
+
+def contract_mpo_mpo(Ks, Ls, maxdim=None, cutoff=None):
+    """K*L (L acts first) as an MPO: M[(aL aK), s, s'', (bL bK)] = sum_{s'} L[aL,s,s',bL] K[aK,s',s'',bK], then the MPS
+    truncation on the fused site index -- [EXT] ``contract(::MPO, ::MPO)``, pinned by test/test_cumpo.jl:145-173."""
+    out = []
+    for Wk, Wl in zip(Ks, Ls):
+        T = np.einsum("astb,ktuc->aksubc", Wl, Wk)
+        a, k, sd, u, b, c = T.shape
+        out.append(T.reshape(a * k, sd, u, b * c, order="F"))
+    if maxdim is None and cutoff is None:
+        return out
+    sd = [(W.shape[1], W.shape[2]) for W in out]
+    mps = truncate([W.reshape(W.shape[0], W.shape[1] * W.shape[2], W.shape[3], order="F") for W in out], maxdim=maxdim,
+                   cutoff=cutoff)
+    return [t.reshape(t.shape[0], d1, d2, t.shape[2], order="F") for t, (d1, d2) in zip(mps, sd)]
+
+
+def add_mpo(Ks, Ls):
+    """[EXT] add(::MPO, ::MPO): direct sum on the fused site index (test/test_cumpo.jl:133-143)."""
+    sd = [(W.shape[1], W.shape[2]) for W in Ks]
+    f = lambda Ws: [W.reshape(W.shape[0], W.shape[1] * W.shape[2], W.shape[3], order="F") for W in Ws]
+    out = add(f(Ks), f(Ls))
+    return [t.reshape(t.shape[0], d1, d2, t.shape[2], order="F") for t, (d1, d2) in zip(out, sd)]
+
+
+def mpo_to_dense(Ws):
+    """dense operator O[(s_1..s_N), (s'_1..s'_N)] of an MPO W[a,s,s',b] (small N only)"""
+    T = Ws[0]                                            # (a, s, s', b)
+    for W in Ws[1:]:
+        T = np.tensordot(T, W, axes=(T.ndim - 1, 0))
+    T = T.reshape(T.shape[1:-1])                         # (s1, s1', s2, s2', ...)
+    n = T.ndim // 2
+    T = np.transpose(T, list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
+    d = int(np.prod(T.shape[:n]))
+    return T.reshape(d, -1)

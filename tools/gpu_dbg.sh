@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/c5_probe.py 2048 gpurun_out/r02_c5_chi2048.json > gpurun_out/c5_2048.log 2>&1; echo "rc=$?"; tail -n 12 gpurun_out/c5_2048.log
-timeout 400 python tools/c5_probe.py 8192 gpurun_out/r02_c5_chi8192.json > gpurun_out/c5_8192.log 2>&1; echo "rc=$?"; tail -n 40 gpurun_out/c5_8192.log
+timeout 300 python -m pytest tests/test_gpu_small_rows.py tests/test_gpu_contract.py tests/test_gpu_vecops.py -q -m gpu --durations=4 > gpurun_out/r02_small.log 2>&1
+echo "rc=$?"; tail -n 60 gpurun_out/r02_small.log
