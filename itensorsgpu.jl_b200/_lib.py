@@ -50,6 +50,7 @@ SIGNATURES = {
     "tnb_plan_cache_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tnb_plan_cache_clear": (_int, [_vp]),
     "tnb_set_autotune": (_int, [_vp, _int]),
+    "tnb_kernel_family_counts": (_int, [_vp, C.POINTER(C.c_uint64)]),
     "tnb_set_workspace_limit": (_int, [_vp, C.c_size_t]),
     "tnb_get_workspace_limit": (C.c_size_t, [_vp]),
     "tnb_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp,
@@ -151,6 +152,12 @@ class Handle:
         v = [C.c_uint64(0) for _ in range(4)]
         self.check(self.lib.tnb_plan_cache_stats(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("entries", "hits", "misses", "autotuned"), [int(x.value) for x in v]))
+
+    def kernel_family_counts(self):
+        """contraction calls per kernel family: {'ldgsts', 'smallk', 'tma'}"""
+        v = (C.c_uint64 * 3)()
+        self.check(self.lib.tnb_kernel_family_counts(self.h, v))
+        return {"ldgsts": int(v[0]), "smallk": int(v[1]), "tma": int(v[2])}
 
     def plan_cache_clear(self):
         self.check(self.lib.tnb_plan_cache_clear(self.h))

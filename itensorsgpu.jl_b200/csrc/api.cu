@@ -10,6 +10,7 @@ void plan_cache_drop(Handle* h);
 void plan_cache_clear(Handle* h);
 void plan_cache_stats(Handle* h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* tuned);
 void plan_cache_set_autotune(Handle* h, int mode);
+void kernel_family_counts(uint64_t out[3]);
 
 int set_err(Handle* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -132,6 +133,12 @@ size_t tnb_workspace_bytes(tnb_handle_t h) { return h ? H->ws_bytes : 0; }
 int tnb_plan_cache_stats(tnb_handle_t h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* autotuned) {
   if (!h) return TNB_ERR_BAD_ARG;
   plan_cache_stats(H, entries, hits, misses, autotuned);
+  return TNB_OK;
+}
+
+int tnb_kernel_family_counts(tnb_handle_t h, uint64_t* out3) {
+  if (!h || !out3) return TNB_ERR_BAD_ARG;
+  kernel_family_counts(out3);
   return TNB_OK;
 }
 

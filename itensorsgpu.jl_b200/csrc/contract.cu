@@ -29,6 +29,9 @@ int launch_tiles_f64(Handle* h, GemmParams& p, bool ak, bool bk, int va, int vb,
 int launch_tiles_c128(Handle* h, GemmParams& p, bool ak, bool bk, int va, int vb, bool small, cudaStream_t st);
 int launch_smallk_f64(Handle* h, GemmParams& p, cudaStream_t st);
 int launch_smallk_c128(Handle* h, GemmParams& p, cudaStream_t st);
+// TMA-staged kernel for operand pairs that are both K-major (contract_tma.cu)
+bool tma_eligible(const GemmParams& p, int dtype, bool small);
+int launch_tma(Handle* h, int dtype, GemmParams& p, bool small, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------
 // Plan cache (the analogue of the reference's `ContractionPlans` dictionary + cuTENSOR autotune,
@@ -46,6 +49,7 @@ struct Variant {
   bool ak = true, bk = true;
   int va = 1, vb = 1;
   bool small = false;
+  bool tma = false;      // both operands K-major and expressible as tensor maps: contract_tma.cu
 };
 struct Plan {
   GemmParams p;
@@ -136,12 +140,19 @@ static Variant choose_variant(Handle* h, int dtype, const GemmParams& p) {
   auto ntiles = [&](int bm, int bn) { return ((long long)(p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * std::max(p.batch, 1); };
   if (!cplx) v.small = ntiles(64, 128) < h->num_sms || p.M <= 64 || p.N <= 64;
   else v.small = ntiles(64, 64) < h->num_sms || p.M <= 64 || p.N <= 32;
+  v.tma = a_k1 && b_k1 && tma_eligible(p, dtype, v.small);
   return v;
 }
 
+// launches per kernel family since load: [0] LDGSTS tile kernel, [1] small-K streaming kernel, [2] TMA kernel calls
+static uint64_t g_family[3] = {0, 0, 0};
+void kernel_family_counts(uint64_t out[3]) { for (int i = 0; i < 3; ++i) out[i] = g_family[i]; }
+
 static int launch_variant(Handle* h, int dtype, GemmParams& p, const Variant& v, cudaStream_t st) {
   const bool cplx = dtype == TNB_C128;
+  g_family[v.smallk ? 1 : (v.tma ? 2 : 0)]++;
   if (v.smallk) return cplx ? launch_smallk_c128(h, p, st) : launch_smallk_f64(h, p, st);
+  if (v.tma) return launch_tma(h, dtype, p, v.small, st);
   if (!cplx) return launch_tiles_f64(h, p, v.ak, v.bk, v.va, v.vb, v.small, st);
   return launch_tiles_c128(h, p, v.ak, v.bk, v.va, v.vb, v.small, st);
 }
@@ -160,7 +171,9 @@ static int autotune_variant(Handle* h, int dtype, GemmParams& p, Variant& v, boo
   // candidates differ only when both tile shapes are sensible: enough tiles for the small one to matter, and not so
   // many that quantisation is irrelevant (> 8 waves of the big tile: keep the big tile)
   const long long big_tiles = ((long long)(p.M + 63) / 64) * ((p.N + (dtype == TNB_C128 ? 63 : 127)) / (dtype == TNB_C128 ? 64 : 128)) * std::max(p.batch, 1);
-  if (v.smallk || !idempotent || flop < 2e9 || big_tiles > 8LL * 2 * h->num_sms || p.M <= 64 || p.N <= 64 || p.npeer > 0)
+  // the TMA form may split K over clusters for its tail wave, a decision tied to the tile shape: its configuration is
+  // never tuned, so that the summation order stays a function of the shape alone
+  if (v.smallk || v.tma || !idempotent || flop < 2e9 || big_tiles > 8LL * 2 * h->num_sms || p.M <= 64 || p.N <= 64 || p.npeer > 0)
     return launch_variant(h, dtype, p, v, st);
   cudaEvent_t e[3];
   for (auto& x : e) TNB_CUDA(h, cudaEventCreate(&x));

@@ -194,4 +194,162 @@ function heff_apply_shard_fused!(out_peers::Vector{Ptr{Cvoid}}, flag_peers::Vect
               out_peers, flag_peers, UInt64(epoch), stream()))
 end
 
+
+# =====================================================================================================
+# Tier 2 -- fused DMRG / TEBD entry points.  These replace the SEQUENCES of tier-1 calls that [EXT] ITensors.jl
+# issues for `product(::ProjMPO, v)`, `makeL!/makeR!`, `KrylovKit.eigsolve`, `noiseterm`, `replacebond!` and one
+# bond of `dmrg` (call sites: examples/dmrg.jl:25, test/dmrg.jl:27,75).  Fixed layouts (column-major CuArrays):
+# phi[l,s1,s2,r], L[l,l',a], R[r,r',c], W[a,s,s',b] (s = ket), A[l,s,r].  `layout(T, inds...)` below is the one
+# permute (tnb_permute_axpby) a maintainer needs when an ITensor's index order differs.
+# =====================================================================================================
+bond_dims(phi::CuArray{<:Any,4}, W1::CuArray{<:Any,4}, W2::CuArray{<:Any,4}) =
+  Ref(BondDims(size(phi, 1), size(phi, 4), size(phi, 2), size(phi, 3), size(W1, 1), size(W1, 4), size(W2, 4)))
+
+"ITensor -> CuArray in the index order `is` (a view when the order already matches, one fused permute otherwise)"
+function layout(T::ITensor, is::Index...)
+  Tp = inds(T) == IndexSet(is...) ? T : permute(T, is...)          # -> tnb_permute_axpby through permute! above
+  return reshape(data(store(tensor(Tp))), dim.(is)...)
+end
+
+# ---- product(::ProjMPO, ::ITensor)  ([EXT] projmpo.jl; four cuTENSOR calls + three allocations in the reference)
+function heff_apply!(out::CuArray{ElT,4}, L::CuArray{ElT,3}, W1::CuArray{ElT,4}, W2::CuArray{ElT,4}, R::CuArray{ElT,3},
+                     phi::CuArray{ElT,4}) where {ElT}
+  check(ccall((:tnb_heff_apply, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), bond_dims(phi, W1, W2), ptr(L), ptr(W1), ptr(W2), ptr(R), ptr(phi), ptr(out), stream()))
+  return out
+end
+
+"drop-in body for `product(P::ProjMPO, v::ITensor)` in the two-site case (P.nsite == 2, both environments present)"
+function product_two_site(P, v::ITensor, l::Index, s1::Index, s2::Index, r::Index)
+  b = P.lpos + 1
+  Lt, Rt = P.LR[P.lpos], P.LR[P.rpos]
+  a, c = commonind(Lt, P.H[b]), commonind(Rt, P.H[b + 1])
+  m = commonind(P.H[b], P.H[b + 1])
+  phi = layout(v, l, s1, s2, r)
+  out = similar(phi)
+  heff_apply!(out, layout(Lt, l, l', a), layout(P.H[b], a, s1, s1', m), layout(P.H[b + 1], m, s2, s2', c),
+              layout(Rt, r, r', c), phi)
+  return itensor(out, l, s1, s2, r)                                 # == noprime(((((v*L)*W1)*W2)*R)
+end
+
+# ---- makeL! / makeR!  ([EXT] projmpo.jl `position!`)
+function env_update_left!(Lnew::CuArray{ElT,3}, L::CuArray{ElT,3}, A::CuArray{ElT,3}, W::CuArray{ElT,4}) where {ElT}
+  check(ccall((:tnb_env_update_left, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), size(A, 1), size(A, 3), size(A, 2), size(W, 1), size(W, 4), ptr(L), ptr(A), ptr(W), ptr(Lnew), stream()))
+  return Lnew
+end
+function env_update_right!(Rnew::CuArray{ElT,3}, R::CuArray{ElT,3}, A::CuArray{ElT,3}, W::CuArray{ElT,4}) where {ElT}
+  check(ccall((:tnb_env_update_right, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), size(A, 1), size(A, 3), size(A, 2), size(W, 1), size(W, 4), ptr(R), ptr(A), ptr(W), ptr(Rnew), stream()))
+  return Rnew
+end
+
+# ---- KrylovKit.eigsolve(PH, phi, 1, :SR; ishermitian=true, tol=1e-14, krylovdim=3, maxiter=1)  ([EXT] dmrg.jl)
+function eigsolve_lanczos!(phi::CuArray{ElT,4}, L, W1, W2, R; krylovdim::Int=3, maxiter::Int=1, tol::Float64=1e-14) where {ElT}
+  e, nmv = Ref{Float64}(0.0), Ref{Cint}(0)
+  check(ccall((:tnb_eigsolve_lanczos, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Float64,
+               Ref{Float64}, Ref{Cint}, Ptr{Cvoid}),
+              handle(), dtype(ElT), bond_dims(phi, W1, W2), ptr(L), ptr(W1), ptr(W2), ptr(R), ptr(phi), krylovdim, maxiter, tol,
+              e, nmv, stream()))
+  return e[], phi, Int(nmv[])                                       # phi overwritten with the normalised Ritz vector
+end
+
+# ---- noiseterm(::ProjMPO, phi, ortho)  ([EXT] projmpo.jl): rho (upper triangle) = noise * nt nt'
+function noise_term!(rho::CuMatrix{ElT}, L, W1, W2, R, phi::CuArray{ElT,4}, ortho::String, noise::Float64;
+                     accumulate::Bool=false) where {ElT}
+  check(ccall((:tnb_noise_term, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Float64, Cint,
+               Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), bond_dims(phi, W1, W2), ptr(L), ptr(W1), ptr(W2), ptr(R), ptr(phi), ortho == "left" ? 0 : 1,
+              noise, accumulate ? 1 : 0, ptr(rho), stream()))
+  return rho
+end
+
+"output capacity of the factorizing calls (include/tnb200.h, tnb_factorize_bond): eigen branch is bounded by the ortho side"
+function kmax_for(m::Int, n::Int, ortho::String, maxdim::Int, eigen_branch::Bool)
+  r = eigen_branch ? (ortho == "left" ? m : n) : min(m, n)
+  return maxdim > 0 ? min(r, maxdim) : r
+end
+
+# ---- replacebond!(psi, b, phi; ortho, which_decomp, maxdim, mindim, cutoff, eigen_perturbation, normalize)
+#      -> factorize  ([EXT] mps.jl / decomp.jl; svd / eigen bodies: src/tensor/culinearalgebra.jl:33-108)
+function factorize_bond!(phi::CuArray{ElT,4}; ortho::String="left", which_decomp::Int=0, maxdim::Int=0, mindim::Int=1,
+                         cutoff::Float64=0.0, rho_pert::Union{Nothing,CuMatrix{ElT}}=nothing, normalize::Bool=false) where {ElT}
+  cl, d1, d2, cr = size(phi)
+  eig = which_decomp == 2 || (which_decomp == 0 && (rho_pert !== nothing || cutoff > 1e-12))
+  k = kmax_for(cl * d1, d2 * cr, ortho, maxdim, eig)
+  A, B = CuArray{ElT}(undef, cl * d1 * k), CuArray{ElT}(undef, k * d2 * cr)
+  nk, err = Ref{Int64}(0), Ref{Float64}(0.0)
+  dims_ = Ref(BondDims(cl, cr, d1, d2, 1, 1, 1))
+  check(ccall((:tnb_factorize_bond, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Float64, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid},
+               Ref{Int64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), dims_, ptr(phi), ortho == "left" ? 0 : 1, which_decomp, maxdim, mindim, cutoff,
+              rho_pert === nothing ? C_NULL : ptr(rho_pert), normalize ? 1 : 0, ptr(A), ptr(B), nk, err, stream()))
+  n = Int(nk[])
+  return reshape(view(A, 1:cl*d1*n), cl, d1, n), reshape(view(B, 1:n*d2*cr), n, d2, cr), Spectrum(nothing, err[])
+end
+
+# ---- one two-site bond of dmrg(): phi = A1*A2, eigsolve, noise term, replacebond!  (ONE call, one sync)
+function dmrg_bond_step!(L, W1, W2, R, A1::CuArray{ElT,3}, A2::CuArray{ElT,3}; ortho::String="left", which_decomp::Int=0,
+                         maxdim::Int, mindim::Int=1, cutoff::Float64=0.0, noise::Float64=0.0, krylovdim::Int=3,
+                         maxiter::Int=1) where {ElT}
+  cl, d1, cm = size(A1); _, d2, cr = size(A2)
+  eig = which_decomp == 2 || (which_decomp == 0 && (noise > 0 || cutoff > 1e-12))
+  k = kmax_for(cl * d1, d2 * cr, ortho, maxdim, eig)
+  b1 = CuArray{ElT}(undef, max(length(A1), cl * d1 * k)); copyto!(b1, 1, vec(A1), 1, length(A1))
+  b2 = CuArray{ElT}(undef, max(length(A2), k * d2 * cr)); copyto!(b2, 1, vec(A2), 1, length(A2))
+  e, nk, err = Ref{Float64}(0.0), Ref{Int64}(0), Ref{Float64}(0.0)
+  dims_ = Ref(BondDims(cl, cr, d1, d2, size(W1, 1), size(W1, 4), size(W2, 4)))
+  check(ccall((:tnb_dmrg_bond_step, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint,
+               Int64, Int64, Float64, Float64, Cint, Cint, Ref{Float64}, Ref{Int64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), dims_, cm, ptr(L), ptr(W1), ptr(W2), ptr(R), ptr(b1), ptr(b2), ortho == "left" ? 0 : 1,
+              which_decomp, maxdim, mindim, cutoff, noise, krylovdim, maxiter, e, nk, err, stream()))
+  n = Int(nk[])
+  return e[], reshape(view(b1, 1:cl*d1*n), cl, d1, n), reshape(view(b2, 1:n*d2*cr), n, d2, cr), err[]
+end
+
+# ---- apply(gate, psi) on sites (n, n+1)  ([EXT] abstractmps.jl `product`; examples/gate_evolution.jl:46)
+function tebd_apply_gate!(G::CuArray{ElT,4}, A1::CuArray{ElT,3}, A2::CuArray{ElT,3}; maxdim::Int=0, mindim::Int=1,
+                          cutoff::Float64=0.0) where {ElT}
+  cl, d1, cm = size(A1); _, d2, cr = size(A2)
+  k = kmax_for(cl * d1, d2 * cr, "left", maxdim, cutoff > 1e-12)
+  b1 = CuArray{ElT}(undef, max(length(A1), cl * d1 * k)); copyto!(b1, 1, vec(A1), 1, length(A1))
+  b2 = CuArray{ElT}(undef, max(length(A2), k * d2 * cr)); copyto!(b2, 1, vec(A2), 1, length(A2))
+  nk, err = Ref{Int64}(0), Ref{Float64}(0.0)
+  check(ccall((:tnb_tebd_apply_gate, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Float64,
+               Ref{Int64}, Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), cl, cm, cr, d1, d2, ptr(G), ptr(b1), ptr(b2), maxdim, mindim, cutoff, nk, err, stream()))
+  n = Int(nk[])
+  return reshape(view(b1, 1:cl*d1*n), cl, d1, n), reshape(view(b2, 1:n*d2*cr), n, d2, cr), err[]
+end
+
+# ---- plan cache / autotune (the `ContractionPlans` dictionary of src/ITensorsGPU.jl:54-55) and workspace limit
+set_autotune(on::Bool) = check(ccall((:tnb_set_autotune, LIB), Cint, (Ptr{Cvoid}, Cint), handle(), on ? 1 : 0))
+set_workspace_limit(bytes::Integer) = check(ccall((:tnb_set_workspace_limit, LIB), Cint, (Ptr{Cvoid}, Csize_t), handle(), bytes))
+
+# ---- multi-GPU peer group (one Julia process per GPU, e.g. under MPI.jl: the 64-byte IPC handles travel by MPI.Allgather)
+function comm_init(rank::Integer, flag_peers::Vector{Ptr{Cvoid}})
+  check(ccall((:tnb_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}), handle(), rank, length(flag_peers), flag_peers))
+end
+function dmrg_bond_step_shard!(Lslab, W1, W2, R, b1::CuVector{ElT}, b2::CuVector{ElT}, dims_::Ref{BondDims}, chiM::Integer,
+                               out_a::Vector{Ptr{Cvoid}}, out_b::Vector{Ptr{Cvoid}}, stage::Vector{Ptr{Cvoid}}; ortho::String="left",
+                               which_decomp::Int=0, maxdim::Int, mindim::Int=1, cutoff::Float64=0.0, noise::Float64=0.0,
+                               krylovdim::Int=3, maxiter::Int=1) where {ElT}
+  e, nk, err = Ref{Float64}(0.0), Ref{Int64}(0), Ref{Float64}(0.0)
+  check(ccall((:tnb_dmrg_bond_step_shard, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint,
+               Int64, Int64, Float64, Float64, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ref{Float64}, Ref{Int64},
+               Ref{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), dims_, chiM, ptr(Lslab), ptr(W1), ptr(W2), ptr(R), ptr(b1), ptr(b2), ortho == "left" ? 0 : 1,
+              which_decomp, maxdim, mindim, cutoff, noise, krylovdim, maxiter, out_a, out_b, stage, e, nk, err, stream()))
+  return e[], Int(nk[]), err[]
+end
+
 end # module

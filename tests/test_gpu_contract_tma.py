@@ -1,0 +1,83 @@
+"""The TMA-staged contraction kernel (csrc/contract_tma.cu: both operands K-major, tensor maps carry the index
+permutation, 128-byte swizzled tiles, mbarrier hand-off, tail-wave split-K over clusters with a distributed-shared-
+memory reduction) against the oracle, with a check that the TMA path (and the split) was really taken."""
+import numpy as np
+import pytest
+
+from gpu_util import check_contract, dev, rand
+from oracle import tensor as ot
+
+pytestmark = pytest.mark.gpu
+
+
+def _tma_calls(h):
+    return h.kernel_family_counts()["tma"]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("case", [
+    # H_eff step 1: K = l (one mode), M = (s1,s2,r) merged, N = (l',a) merged
+    dict(dims=dict(l=256, s1=2, s2=2, r=192, lp=256, a=5), la=("l", "s1", "s2", "r"), lb=("l", "lp", "a")),
+    # H_eff step 4: K = (r, c) -- two modes, 3-D maps
+    dict(dims=dict(r=192, lp=128, s1p=2, s2p=2, c=5, rp=192), la=("r", "lp", "s1p", "s2p", "c"), lb=("r", "rp", "c")),
+    # ragged M and N (zero-filled out-of-bounds rows of the last tiles), K a multiple of 16
+    dict(dims=dict(k=208, m=203, n=333), la=("k", "m"), lb=("k", "n")),
+    # unmergeable M modes: C order separates them, first M extent a multiple of the tile height
+    dict(dims=dict(k=128, m0=128, m1=3, n=160), la=("k", "m0", "m1"), lb=("k", "n"), lc=("m0", "n", "m1")),
+    # K spread over three modes (4-D maps)
+    dict(dims=dict(k0=32, k1=3, k2=4, m=192, n=256), la=("k0", "m", "k1", "k2"), lb=("k0", "k2", "n", "k1")),
+])
+def test_tma_contraction_cases(case, cplx):
+    from itensorsgpu_b200 import tn
+    h = tn.handle()
+    n0 = _tma_calls(h)
+    rng = np.random.default_rng(91)
+    check_contract(rng, case["dims"], case["la"], case["lb"], cplx, lc=case.get("lc"))
+    check_contract(rng, case["dims"], case["la"], case["lb"], cplx, lc=case.get("lc"), alpha=0.7, beta=-1.3,
+                   conj_a=cplx, conj_b=True)
+    assert _tma_calls(h) == n0 + 2, "the TMA-staged kernel was not selected"
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("K,launches", [(1024, 2), (256 + 16 * 7, 2), (64, 1)])
+def test_tma_tail_wave_split_k(K, launches, cplx):
+    """304 (complex: 608 of the 64x64) tiles on 296 CTA slots: one full wave + a tail of 8 (16) tiles, which runs as
+    clusters of 4 (K >= 512) or 2 CTAs splitting K and reducing through distributed shared memory; K = 64 is too
+    short to split.  Deterministic: two runs are bit-identical."""
+    from itensorsgpu_b200 import tn
+    h = tn.handle()
+    rng = np.random.default_rng(92)
+    M, N = 64 * 19, 128 * 16
+    if cplx:
+        N = 64 * 32
+    A = rand(rng, (K, M), cplx); B = rand(rng, (K, N), cplx)
+    dA, dB = dev(A), dev(B)
+    h.plan_cache_clear()
+    l0, t0 = h.launches, _tma_calls(h)
+    out1 = tn.ops.contract(dA, ("k", "m"), dB, ("k", "n"))[0].numpy()
+    assert h.launches - l0 == launches and _tma_calls(h) == t0 + 1
+    out2 = tn.ops.contract(dA, ("k", "m"), dB, ("k", "n"))[0].numpy()
+    assert np.array_equal(out1, out2)
+    assert ot.rel_err(out1, A.T @ B) < 1e-12
+
+
+def test_tma_and_ldgsts_kernels_agree_bitwise_without_split():
+    """Same k order in both kernels: when no tail split applies the two families produce identical bits (what lets
+    the plan choice stay invisible in the results)."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, hashlib\n"
+            "from itensorsgpu_b200 import tn\n"
+            "rng = np.random.default_rng(5)\n"
+            "A = tn.DTensor.from_numpy(rng.standard_normal((512, 592))); B = tn.DTensor.from_numpy(rng.standard_normal((512, 1024)))\n"
+            "o = tn.ops.contract(A, ('k', 'm'), B, ('k', 'n'))[0].numpy()\n"
+            "print(hashlib.sha256(o.tobytes()).hexdigest(), tn.handle().kernel_family_counts()['tma'])\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"TNB_TMA": "off"}):
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.split())
+    assert outs[0][1] == "1" and outs[1][1] == "0"
+    assert outs[0][0] == outs[1][0]
