@@ -32,6 +32,7 @@ int launch_smallk_c128(Handle* h, GemmParams& p, cudaStream_t st);
 // TMA-staged kernel for operand pairs that are both K-major (contract_tma.cu)
 bool tma_eligible(const GemmParams& p, int dtype, bool small);
 int launch_tma(Handle* h, int dtype, GemmParams& p, bool small, cudaStream_t st);
+bool tma_would_split(Handle* h, const GemmParams& p, int dtype, bool small);
 
 // ------------------------------------------------------------------------------------
 // Plan cache (the analogue of the reference's `ContractionPlans` dictionary + cuTENSOR autotune,
@@ -162,27 +163,38 @@ static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) 
   return launch_variant(h, dtype, p, v, st);
 }
 
-// One-shot autotune of a new shape: time the two tile configurations on the caller's operands (beta = 0 only: the
-// call is then idempotent) and keep the faster.  Returns with C holding the result.
+// One-shot autotune of a new shape: time the candidate variants on the caller's operands (beta = 0 only: the call is
+// then idempotent) and keep the fastest.  Candidates never differ in the bits they produce:
+//   * TMA-eligible shape whose tail wave is not split: TMA-staged kernel vs LDGSTS kernel, same tile (the two families
+//     share the k order; measured at chi = 4096: step 1 is 2.5% faster through TMA, step 4 2.8% faster through LDGSTS);
+//   * TMA-eligible shape WITH a split tail: never tuned (the split changes the summation order and is a function of
+//     the shape alone);
+//   * other shapes: large vs small tile of the LDGSTS kernel.
+// Returns with C holding the result.
 static int autotune_variant(Handle* h, int dtype, GemmParams& p, Variant& v, bool* tuned, cudaStream_t st) {
   *tuned = false;
   const double flop = 2.0 * p.M * (double)p.N * p.K * std::max(p.batch, 1) * (dtype == TNB_C128 ? 4 : 1);
   const bool idempotent = p.beta_re == 0.0 && p.beta_im == 0.0;
-  // candidates differ only when both tile shapes are sensible: enough tiles for the small one to matter, and not so
-  // many that quantisation is irrelevant (> 8 waves of the big tile: keep the big tile)
-  const long long big_tiles = ((long long)(p.M + 63) / 64) * ((p.N + (dtype == TNB_C128 ? 63 : 127)) / (dtype == TNB_C128 ? 64 : 128)) * std::max(p.batch, 1);
-  // the TMA form may split K over clusters for its tail wave, a decision tied to the tile shape: its configuration is
-  // never tuned, so that the summation order stays a function of the shape alone
-  if (v.smallk || v.tma || !idempotent || flop < 2e9 || big_tiles > 8LL * 2 * h->num_sms || p.M <= 64 || p.N <= 64 || p.npeer > 0)
-    return launch_variant(h, dtype, p, v, st);
-  cudaEvent_t e[3];
+  if (v.smallk || !idempotent || flop < 2e9 || p.M <= 64 || p.N <= 64) return launch_variant(h, dtype, p, v, st);
+  Variant cands[2] = {v, v};
+  if (v.tma) {
+    if (tma_would_split(h, p, dtype, v.small)) return launch_variant(h, dtype, p, v, st);
+    cands[1].tma = false;
+  } else {
+    // tile shapes differ only when both are sensible: enough tiles for the small one to matter, and not so many that
+    // quantisation is irrelevant (> 8 waves of the big tile: keep the big tile)
+    const long long big_tiles = ((long long)(p.M + 63) / 64) * ((p.N + (dtype == TNB_C128 ? 63 : 127)) / (dtype == TNB_C128 ? 64 : 128)) * std::max(p.batch, 1);
+    if (big_tiles > 8LL * 2 * h->num_sms || p.npeer > 0) return launch_variant(h, dtype, p, v, st);
+    cands[0].small = false;
+    cands[1].small = true;
+  }
+  cudaEvent_t e[2];
   for (auto& x : e) TNB_CUDA(h, cudaEventCreate(&x));
   float best = 1e30f;
   int rc = TNB_OK;
   Variant bestv = v;
   for (int cand = 0; cand < 2 && !rc; ++cand) {
-    Variant c = v;
-    c.small = cand == 1;
+    const Variant& c = cands[cand];
     rc = launch_variant(h, dtype, p, c, st);                 // warm (instruction cache, L2)
     if (rc) break;
     cudaEventRecord(e[0], st);

@@ -15,8 +15,9 @@
 //     of a half-warp hit 32 distinct banks once the 8 rows of a DMMA fragment are taken in the order 0,2,4,6,1,3,5,7
 //     (complex: 0,4,1,5,2,6,3,7 for the 128-bit loads of a quarter-warp) -- a relabelling of rows/columns inside the
 //     8x8 DMMA tile that the epilogue undoes.  No padding: 24 KB per stage, 4 stages, 2 CTAs per SM.
-//   * mbarrier hand-off: the producer arms full[s] with the byte count, consumers wait on its phase; slot reuse is
-//     ordered by the CTA barrier at the top of each k-tile.
+//   * mbarrier hand-off both ways: the producer arms full[s] with the byte count and consumers wait on its phase; each
+//     warp releases a stage on empty[s] once its DMMAs have consumed the last fragment, and the producer refills the
+//     slot two k-tiles ahead.  There is no CTA-wide barrier in the main loop.
 //   * Tail-wave split-K over thread-block clusters: when the last wave of tiles would leave most of the 296 CTA slots
 //     idle (H_eff step 4 of an 8-way shard: 1024 tiles = 3.46 waves), the tiles of that wave are launched as clusters
 //     of 2 or 4 CTAs that each take a K range and reduce through distributed shared memory in a fixed order
@@ -28,6 +29,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "tnb_internal.h"
 
@@ -117,7 +119,7 @@ struct TCfg {
   static constexpr int SMEM = ST * STAGE_BYTES + 1024;      // + slack for the 1024-byte alignment of the swizzle atom
 };
 
-template <bool CPLX, class CFG>
+template <bool CPLX, class CFG, int PD_>
 __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB,
                                                                    const __grid_constant__ GemmParams p,
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
   static_assert(NACC * NT * 8 <= ST * STAGE_BYTES, "split-K reduction buffer must fit the stage ring");
 
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long full_bar[ST];
+  __shared__ __align__(8) unsigned long long full_bar[2 * ST];      // full[0..ST), empty[ST..2ST)
   const unsigned smem_u32 = ((unsigned)__cvta_generic_to_shared(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (smem_u32 - (unsigned)__cvta_generic_to_shared(smem_raw));
   const unsigned bar0 = (unsigned)__cvta_generic_to_shared(full_bar);
@@ -169,9 +171,14 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
   }
   const int nIt = kt1 - kt0;
 
+  constexpr int PD = PD_;                               // prefetch distance in k-tiles (ST - 2: refill never waits on the tile just finished)
+  constexpr int NWARP = NT / 32;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < ST; ++s) mbar_init(bar0 + 8 * s, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(bar0 + 8 * s, 1);                       // full[s]:  the producer's arrive + the bytes of both boxes
+      mbar_init(bar0 + 8 * (ST + s), NWARP);            // empty[s]: one arrive per consumer warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -211,6 +218,8 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
   auto issue = [&](int it) {          // thread 0 only: k-tile kt0 + it into slot it % ST
     const int s = it % ST;
     const unsigned bar = bar0 + 8 * s;
+    // the slot's previous occupant (k-tile it - ST) must have been read by every warp
+    if (it >= ST) mbar_wait(bar0 + 8 * (ST + s), (unsigned)(((it / ST) - 1) & 1));
     set_k(kt0 + it);
     mbar_expect_tx(bar, STAGE_BYTES);
     tma_load(smem_u32 + s * STAGE_BYTES, &mapA, bar, ra, ca);
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
   };
   if (tid == 0) {
 #pragma unroll 1
-    for (int it = 0; it < ST - 1 && it < nIt; ++it) issue(it);
+    for (int it = 0; it < PD && it < nIt; ++it) issue(it);
   }
 
   double acc[MI][NI][CPLX ? 4 : 2];
@@ -231,6 +240,7 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
 
   const double sa = p.conjA ? -1.0 : 1.0, sb = p.conjB ? -1.0 : 1.0;
   constexpr int KK = BK / 4;
+  static_assert(KK % 2 == 0, "fragment double buffer assumes an even number of k-steps per tile");
   // byte offsets inside a 128-byte row of this thread's k for every k-step (swizzle: 16-byte chunk index ^ (row & 7))
   int koff[KK];
 #pragma unroll
@@ -240,50 +250,47 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
   }
   const int arow = (wm0 + fr) * 128, brow = (wn0 + fr) * 128;
 
+  // No CTA-wide barrier in the main loop: warps run ahead of one another as far as the stage ring allows, so their
+  // tile-boundary bubbles (barrier wait + first fragment loads) do not line up across the 2 warps of an SMSP -- with a
+  // __syncthreads per k-tile the DMMA pipe idled 7.7% (ncu, same as round 1's LDGSTS kernel).  The fragments of the
+  // first k-step of tile it+1 are loaded during the last k-step of tile it.
+  using Frag = typename std::conditional<CPLX, double2, double>::type;
+  Frag a[2][MI], b[2][NI];
+  auto ldfrag = [&](const unsigned char* sA, int kk, Frag* fa, Frag* fb) {
+    const unsigned char* sB = sA + A_BYTES;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      fa[i] = *reinterpret_cast<const Frag*>(sA + arow + i * 1024 + koff[kk]);
+      if constexpr (CPLX) fa[i].y *= sa;
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      fb[j] = *reinterpret_cast<const Frag*>(sB + brow + j * 1024 + koff[kk]);
+      if constexpr (CPLX) fb[j].y *= sb;
+    }
+  };
+  if (nIt > 0) {
+    mbar_wait(bar0, 0u);
+    ldfrag(smem, 0, a[0], b[0]);
+  }
 #pragma unroll 1
   for (int it = 0; it < nIt; ++it) {
-    mbar_wait(bar0 + 8 * (it % ST), (unsigned)((it / ST) & 1));
-    __syncthreads();                  // every warp is done with k-tile it-1: its slot may be refilled
-    if (tid == 0 && it + ST - 1 < nIt) issue(it + ST - 1);
+    if (tid == 0 && it + PD < nIt) issue(it + PD);
     const unsigned char* sA = smem + (it % ST) * STAGE_BYTES;
-    const unsigned char* sB = sA + A_BYTES;
-    if (!CPLX) {
-      double a[2][MI], b[2][NI];
-      auto ldfrag = [&](int kk, double* fa, double* fb) {
 #pragma unroll
-        for (int i = 0; i < MI; ++i) fa[i] = *reinterpret_cast<const double*>(sA + arow + i * 1024 + koff[kk]);
+    for (int kk = 0; kk < KK; ++kk) {
+      if (kk + 1 < KK) {
+        ldfrag(sA, kk + 1, a[(kk + 1) & 1], b[(kk + 1) & 1]);
+      } else if (it + 1 < nIt) {
+        mbar_wait(bar0 + 8 * ((it + 1) % ST), (unsigned)(((it + 1) / ST) & 1));
+        ldfrag(smem + ((it + 1) % ST) * STAGE_BYTES, 0, a[0], b[0]);
+      }
 #pragma unroll
-        for (int j = 0; j < NI; ++j) fb[j] = *reinterpret_cast<const double*>(sB + brow + j * 1024 + koff[kk]);
-      };
-      ldfrag(0, a[0], b[0]);
-#pragma unroll
-      for (int kk = 0; kk < KK; ++kk) {
-        if (kk + 1 < KK) ldfrag(kk + 1, a[(kk + 1) & 1], b[(kk + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < MI; ++i)
+      for (int i = 0; i < MI; ++i) {
+        if constexpr (!CPLX) {
 #pragma unroll
           for (int j = 0; j < NI; ++j) tdmma(acc[i][j][0], acc[i][j][1], a[kk & 1][i], b[kk & 1][j]);
-      }
-    } else {
-      double2 a[2][MI], b[2][NI];
-      auto ldfrag = [&](int kk, double2* fa, double2* fb) {
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
-          fa[i] = *reinterpret_cast<const double2*>(sA + arow + i * 1024 + koff[kk]);
-          fa[i].y *= sa;
-        }
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          fb[j] = *reinterpret_cast<const double2*>(sB + brow + j * 1024 + koff[kk]);
-          fb[j].y *= sb;
-        }
-      };
-      ldfrag(0, a[0], b[0]);
-#pragma unroll
-      for (int kk = 0; kk < KK; ++kk) {
-        if (kk + 1 < KK) ldfrag(kk + 1, a[(kk + 1) & 1], b[(kk + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
+        } else {
           const double2 av = a[kk & 1][i];
           const double nai = -av.y;
 #pragma unroll
@@ -297,6 +304,9 @@ __global__ void __launch_bounds__(CFG::NT, 2) contract_tma_kernel(const __grid_c
         }
       }
     }
+    // every fragment of this stage has been consumed by a DMMA (its loads have completed): release the slot
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar0 + 8 * (ST + it % ST)) : "memory");
   }
 
   // ---- split-K: ranks 1.. of the cluster hand their accumulators to rank 0 through distributed shared memory
@@ -484,9 +494,31 @@ static int make_map(Handle* h, CUtensorMap* map, const Group& gk, const Group& g
   return TNB_OK;
 }
 
+// tail wave: when the last partial wave wastes more than 10% of the launch, its tiles run as clusters of 2 or 4 CTAs
+// that split K (a function of the shape only: every rank / every run sums in the same order)
+static int tail_split(Handle* h, const GemmParams& p, long long tiles, int KT) {
+  static const bool nosplit = getenv("TNB_SPLITK") && !strcmp(getenv("TNB_SPLITK"), "off");
+  const long long slots = 2LL * h->num_sms;
+  const long long fullw = tiles / slots, rem = tiles - fullw * slots;
+  if (nosplit || rem == 0 || p.lowerOnly) return 1;
+  const double eff = (double)tiles / (double)((fullw + 1) * slots);
+  if (eff >= 0.9) return 1;
+  if (rem * 4 <= slots && KT >= 32) return 4;
+  if (rem * 2 <= slots && KT >= 16) return 2;
+  return 1;
+}
+
+bool tma_would_split(Handle* h, const GemmParams& p, int dtype, bool small) {
+  const bool cplx = dtype == TNB_C128;
+  const int bm = 64, bn = cplx ? (small ? 32 : 64) : (small ? 64 : 128), bk = cplx ? 8 : 16;
+  const long long tiles = ((long long)(p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn);
+  return tail_split(h, p, tiles, p.K / bk) > 1;
+}
+
 template <bool CPLX, class CFG>
 static int launch_tma_cfg(Handle* h, GemmParams& p, cudaStream_t st) {
-  auto kern = contract_tma_kernel<CPLX, CFG>;
+  static const int pd = getenv("TNB_TMA_PD") ? atoi(getenv("TNB_TMA_PD")) : 2;
+  auto kern = pd == 3 ? contract_tma_kernel<CPLX, CFG, 3> : contract_tma_kernel<CPLX, CFG, 2>;
   static bool attr_done = false;
   if (!attr_done) {
     TNB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));
@@ -503,20 +535,9 @@ static int launch_tma_cfg(Handle* h, GemmParams& p, cudaStream_t st) {
   TNB_TRY(make_map(h, &mapB, p.gk, p.gn, true, CFG::BN, BK, CPLX, p.B));
   TmaExtra x;
   x.nkm = p.gk.n; x.nmm = p.gm.n; x.nnm = p.gn.n;
-  // tail wave: when the last partial wave wastes more than 10% of the launch, run its tiles as clusters of 2 or 4 CTAs
-  // that split K (a function of the shape only: every rank / every run sums in the same order)
-  static const bool nosplit = getenv("TNB_SPLITK") && !strcmp(getenv("TNB_SPLITK"), "off");
   const long long slots = 2LL * h->num_sms;
   const long long fullw = tiles / slots, rem = tiles - fullw * slots;
-  const int KT = p.K / BK;
-  int ks = 1;
-  if (!nosplit && rem > 0 && !p.lowerOnly) {
-    const double eff = (double)tiles / (double)((fullw + 1) * slots);
-    if (eff < 0.9) {
-      if (rem * 4 <= slots && KT >= 32) ks = 4;
-      else if (rem * 2 <= slots && KT >= 16) ks = 2;
-    }
-  }
+  const int ks = tail_split(h, p, tiles, p.K / BK);
   auto launch = [&](long long first, long long count, int ksplit) -> int {
     if (count <= 0) return TNB_OK;
     x.tileOffset = (int)first; x.nTiles = (int)count; x.kSplit = ksplit;

@@ -32,12 +32,14 @@ def test_dmrg_spin_one_heisenberg_energy_parity():
     e, psi = tn.dmrg(tn.cu(_host_mpo(tn, Ws)), tn.cu(_host_mps(tn, psi0)), tn.Sweeps(3, **kw),
                      observer=lambda sw, b, o, en, err: hist.append(en) if (o == "right" and b == 0) else None)
     assert e < -12.0                                          # the reference's assertion
-    # SU(2) multiplets make the Schmidt spectrum degenerate at the cut, so WHICH vector of a multiplet
-    # survives a cutoff-1e-11 truncation is implementation-defined (LAPACK syevr vs Jacobi): energies
-    # agree to the truncation error, not beyond.  The strict 1e-10 bar is test_dmrg_exact_regime below.
+    # Why not 1e-10 on this workload (measured in tests/test_gpu_dmrg_lockstep.py): with the noise term rho carries a
+    # cluster of noise-lifted eigenvalues ~1e-10 whose eigenVECTORS two backward-stable eigensolvers (LAPACK syevr, the
+    # GPU's divide & conquer) resolve only to an angle eps*|rho|/gap_abs ~ 1e-5.  They carry ~1e-10 of the weight of the
+    # current two-site tensor (which agrees to 1e-11 bond by bond, as do all energies when the oracle is forced onto the
+    # GPU's trajectory) but they span the next bond's variational space, so free-running energies differ at the 1e-6
+    # level while the sweeps are unconverged and re-converge afterwards (5 sweeps: 1e-10).
     assert abs(e - e_ref) < 5e-9
-    # sweeps 1-2 (maxdim 10 / 20 binding) cut through multiplets: per-sweep agreement is bounded by their
-    # truncation error (1e-6-class), the final sweep (maxdim 40, cutoff-limited) by 5e-9
+    # sweeps 1-2 (unconverged): 1e-6-class; the final sweep: 5e-9
     assert np.max(np.abs(np.array(hist) - np.array(hist_ref))) < 2e-6
     # the returned state reproduces the energy
     H = tn.cu(_host_mpo(tn, Ws))
