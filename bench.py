@@ -294,6 +294,7 @@ def tebd_c4(tn, world, rank, chi=2048, nsites=128, warm_gates=True):
     kw = dict(maxdim=chi, cutoff=1e-12)
     if world > 1:
         sh = tn.tebd.ShardedTEBD(st, nsites)
+        sh.warm_links()        # NCCL opens its point-to-point channels on first use: not part of a layer
         layer = lambda p: sh.layer(Gd, p, **kw)
     else:
         layer = lambda p: tn.tebd.tebd_layer(st, Gd, p, **kw)
@@ -522,9 +523,10 @@ def run_gpu(args):
         if world == 1:
             herr = float((oh.cuda() - res.data).norm() / res.data.norm())
         elif comm is not None:
-            lo = rank * clp
-            mine = oh.view(D * D * chi, chi)[:, lo:lo + clp].cuda()
-            want = res.data.view(D * D * chi, chi)[:, lo:lo + clp]
+            r0, r1 = hh.chunk_range()
+            col = chi * D * D
+            mine = oh[r0 * col:r1 * col].cuda()
+            want = res.data[r0 * col:r1 * col]
             herr = max_over_ranks(float((mine - want).norm() / want.norm()))
         else:
             herr = None
@@ -596,7 +598,9 @@ def run_gpu(args):
                                                                        if args.shard == "lp" else "x%d; %s" % (world, gather_mode))},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "contract_kernel<f64> on H_eff steps 1 and 4 (M=%d, N=%d, K=%d per launch)" % (D * D * chi, clp * W, chi),
+                         "kernel": "DMMA contraction kernels on H_eff steps 1 and 4 (M=%d, N=%d, K=%d per launch); the plan cache "
+                                   "picks the TMA-staged (contract_tma_kernel) or the LDGSTS form (contract_kernel) per shape" % (D * D * chi, clp * W, chi),
+                         "kernel_family_calls": h.kernel_family_counts(), "plan_cache": h.plan_cache_stats(),
                          "flop_per_launch": flops_per_launch, "ms_per_launch": kern_s * 1e3, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": F / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -348,9 +348,10 @@ int tnb_dmrg_bond_step_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* d, 
 }
 
 // End-to-end sharded matvec with HOST buffers (bench.py `e2e` at N > 1).  Every rank uploads only ITS r-chunk of phi
-// (1/world of the vector over PCIe), forwards it to the peers over NVLink, runs its slab of the matvec with the
-// all-gather fused into step 4, and downloads only ITS l' slab of H*phi (a strided window of out_host, which has
-// phi's layout) -- whole job: one vector up, one vector down, everything else over NVLink.  Synchronous.
+// (1/world of the vector over PCIe), forwards it to the peers over NVLink, runs its l' slab of the matvec with the
+// all-gather fused into step 4 (after which every rank holds the full H*phi), and downloads only ITS r'-chunk of H*phi
+// (contiguous, like the upload: r is the slowest mode) -- whole job: one vector up, one vector down, everything else
+// over NVLink.  Synchronous.
 int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* d, const void* L_slab, const void* W1,
                               const void* W2, const void* R, const void* phi_host, void* const* phi_peers,
                               void* const* out_peers, void* out_host, void* stream) {
@@ -362,6 +363,7 @@ int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* d,
   const int rank = H->comm.rank, world = H->comm.world;
   const size_t es = elsize(dtype);
   const int64_t cl = d->chiL, cr = d->chiR, clp = cl / world;
+  (void)es;
   const size_t col = (size_t)cl * d->d1 * d->d2 * es;                  // bytes of phi per unit of r
   const int64_t rc = (cr + world - 1) / world;
   const int64_t r0 = std::min<int64_t>(cr, rank * rc), r1 = std::min<int64_t>(cr, r0 + rc);
@@ -383,9 +385,9 @@ int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* d,
   TNB_TRY(comm_barrier(H, ST));                                       // the full phi is on every rank
   TNB_TRY(heff_shard_fused_core(H, dtype, d, rank, world, clp, L_slab, W1, W2, R, phi_peers[rank], out_peers, t0, t1, ST));
   TNB_TRY(comm_barrier(H, ST));
-  TNB_CUDA(H, cudaMemcpy2DAsync((char*)out_host + (size_t)rank * clp * es, (size_t)cl * es,
-                                (const char*)out_peers[rank] + (size_t)rank * clp * es, (size_t)cl * es, (size_t)clp * es,
-                                (size_t)d->d1 * d->d2 * cr, cudaMemcpyDeviceToHost, ST));
+  if (r1 > r0)
+    TNB_CUDA(H, cudaMemcpyAsync((char*)out_host + r0 * col, (const char*)out_peers[rank] + r0 * col, (r1 - r0) * col,
+                                cudaMemcpyDeviceToHost, ST));
   return check_cuda(H, cudaStreamSynchronize(ST), "heff_apply_shard_host sync");
 }
 

@@ -301,7 +301,7 @@ class ShardedHeffHost:
 
     def apply_host(self, Lslab, W1, W2, R, phi_host, out_host):
         """phi_host / out_host: pinned CPU tensors in phi's layout; only this rank's r-chunk of phi_host is read and
-        only its l' slab of out_host is written.  Synchronous."""
+        only its r'-chunk of out_host is written (``chunk_range``).  Synchronous."""
         import ctypes as C
         from . import ops
         from .ops import BondDims
@@ -312,6 +312,13 @@ class ShardedHeffHost:
                                                 ops._ptr(W2.data), ops._ptr(R.data), ops._ptr(phi_host), self.phis.c_array(),
                                                 self.outs.c_array(), ops._ptr(out_host), ops._stream()))
         return out_host
+
+    def chunk_range(self):
+        """[r0, r1): the slice of the slowest mode r this rank moves over PCIe"""
+        cr, w, g = self.dims[3], self.comm.world, self.comm.rank
+        rc = (cr + w - 1) // w
+        r0 = min(cr, g * rc)
+        return r0, min(cr, r0 + rc)
 
     def device_result(self):
         """DTensor view of the full H*phi in this rank's own result buffer (after apply_host)."""

@@ -157,6 +157,22 @@ class ShardedTEBD:
         d.recv(v, src, group=self.group)
         return v.to(device)
 
+    def warm_links(self):
+        """Exchange one element with each neighbour: NCCL opens its point-to-point channels lazily (seconds on the
+        first send/recv), which would otherwise be charged to the first odd layer."""
+        dev = self.state.Bs[0].data.device
+        one = torch.zeros(1, dtype=torch.float64, device=dev)
+        pending = []
+        if self.rank > 0:
+            pending += self._send_vec(one, self.rank - 1)
+        if self.rank < self.world - 1:
+            self._recv_vec(self.rank + 1, dev)
+            pending += self._send_vec(one, self.rank + 1)
+        if self.rank > 0:
+            self._recv_vec(self.rank - 1, dev)
+        for p in pending:
+            p.wait()
+
     def layer(self, G, parity, maxdim=None, cutoff=0.0):
         """One even (0) or odd (1) layer over the whole chain; returns this rank's largest truncation error."""
         st = self.state

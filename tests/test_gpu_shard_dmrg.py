@@ -92,19 +92,19 @@ def _w_lanczos_and_host(rank, world, comm, cplx):
                                              sh.out_a.c_array(), sh.out_b.c_array(), 3, 1, 1e-14, C.byref(e2), C.byref(n2),
                                              tn.ops._stream()))
     errs = [abs(e1 - e2.value) / abs(e1), ot.rel_err(p2.numpy(), p1.numpy()), float(n1 != n2.value)]
-    # end-to-end host-buffer matvec: this rank's r-chunk up, this rank's l' slab down
+    # end-to-end host-buffer matvec: this rank's r-chunk up, this rank's r'-chunk down
     hh = tn.shard.ShardedHeffHost(comm, (cl, d, d, cr), dt)
     ph = torch.from_numpy(np.ascontiguousarray(phi.ravel(order="F"))).pin_memory()
     oh = torch.zeros_like(ph).pin_memory()
     want = od.heff_apply(L, W1, W2, R, phi)
-    lo, hi = tn.shard.slab_range(cl, rank, world)
+    lo, hi = hh.chunk_range()
     for rep in range(2):
         oh.zero_()
         hh.apply_host(Ls, D(W1), D(W2), D(R), ph, oh)
         got = oh.numpy().reshape((cl, d, d, cr), order="F")
-        errs.append(ot.rel_err(got[lo:hi], want[lo:hi]))
-        mask = np.ones(cl, bool); mask[lo:hi] = False
-        errs.append(float(np.abs(got[mask]).max()) if mask.any() else 0.0)       # nothing outside the slab is written
+        errs.append(ot.rel_err(got[..., lo:hi], want[..., lo:hi]))
+        mask = np.ones(cr, bool); mask[lo:hi] = False
+        errs.append(float(np.abs(got[..., mask]).max()) if mask.any() else 0.0)  # nothing outside the chunk is written
         errs.append(ot.rel_err(hh.device_result().numpy(), want))                # the device copy is the full vector
     comm.status()
     return max(errs)

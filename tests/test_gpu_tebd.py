@@ -92,6 +92,7 @@ def _worker(rank, world):
     Gd = tn.DTensor.from_numpy(G)
     full = tn.tebd.canonical_form(tn.cu(tn.MPS(psi, llim=-1, rlim=1)))
     sh = tn.tebd.ShardedTEBD.scatter_from(full, N)
+    sh.warm_links()
     for step in range(2):
         sh.layer(Gd, 0, maxdim=12)
         sh.layer(Gd, 1, maxdim=12)

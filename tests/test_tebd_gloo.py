@@ -40,6 +40,7 @@ def _worker(rank, world, port, q, N):
     f = lambda a: tn.DTensor(torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))), a.shape)
     full = tn.tebd.BState([f(b) for b in Bs], [torch.from_numpy(l.copy()) for l in lams])
     sh = tn.tebd.ShardedTEBD.scatter_from(full, N, gate_fn=_oracle_gate(tn))
+    sh.warm_links()
     Gd = f(G)
     for _ in range(2):
         sh.layer(Gd, 0, maxdim=10)

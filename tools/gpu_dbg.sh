@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-export TNB_TEST_TRACE=$PWD/gpurun_out
-timeout 300 python -m pytest tests/test_gpu_dmrg_lockstep.py -q -m gpu > gpurun_out/r02_lock.log 2>&1
-echo "rc=$?"; tail -n 5 gpurun_out/r02_lock.log
+t0=$(date +%s)
+timeout 900 python bench.py > gpurun_out/r02_bench_full.json 2> gpurun_out/r02_bench_full.err
+echo "bench full rc=$? ($(( $(date +%s) - t0 )) s)"; tail -n 3 gpurun_out/r02_bench_full.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-sweep --no-tebd --no-cpu-baseline > gpurun_out/r02_bench_under_ncu.log 2>&1
+echo "ncu rc=$?"
