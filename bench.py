@@ -498,7 +498,7 @@ def run_gpu(args):
         comm = tn.shard.ShardComm()
         hh = tn.shard.ShardedHeffHost(comm, phi.dims, torch.float64)
         e2e_step = lambda: hh.apply_host(L, W1, W2, R, ph, oh)
-        e2e_api = "tnb_heff_apply_shard_host (per rank: 1/N of phi up, 1/N of H*phi down; NVLink for the rest)"
+        e2e_api = "tnb_heff_apply_shard_host (per rank: 1/N of phi up, its own 1/N of H*phi down overlapped with step 4; NVLink for the rest)"
         h2d = d2h = nbytes          # whole job: exactly one vector each way
     else:
         def e2e_step():
@@ -523,10 +523,9 @@ def run_gpu(args):
         if world == 1:
             herr = float((oh.cuda() - res.data).norm() / res.data.norm())
         elif comm is not None:
-            r0, r1 = hh.chunk_range()
-            col = chi * D * D
-            mine = oh[r0 * col:r1 * col].cuda()
-            want = res.data[r0 * col:r1 * col]
+            lo = rank * clp
+            mine = oh.view(D * D * chi, chi)[:, lo:lo + clp].cuda()
+            want = res.data.view(D * D * chi, chi)[:, lo:lo + clp]
             herr = max_over_ranks(float((mine - want).norm() / want.norm()))
         else:
             herr = None

@@ -274,8 +274,8 @@ int tnb_dmrg_bond_step_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* dim
 /* End-to-end sharded matvec with HOST buffers (bench.py `e2e` at N > 1): this rank uploads only its r-chunk of
  * phi_host (1/world of the vector; chunk g = r in [g*ceil(chiR/world), ...)), forwards it to the peer-mapped phi
  * buffers of all ranks over NVLink, runs its l' slab with the all-gather fused into step 4 (every rank then holds the
- * full H*phi on the device), and downloads only its r'-chunk of H*phi into out_host (same chunking as the upload;
- * phi_host / out_host have phi's layout).  Synchronous. */
+ * full H*phi on the device), and downloads only its own l' slab of H*phi into out_host (a strided window: phi_host /
+ * out_host have phi's layout), piece by piece over r' while the next piece is being computed.  Synchronous. */
 int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, const void* L_slab, const void* W1,
                               const void* W2, const void* R, const void* phi_host, void* const* phi_peers,
                               void* const* out_peers, void* out_host, void* stream);

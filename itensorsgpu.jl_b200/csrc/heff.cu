@@ -149,7 +149,7 @@ struct PeerOut {           // fused all-gather of the sharded result (step 4 epi
 
 static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, const void* L, const void* W1,
                      const void* W2, const void* R, const void* phi, void* out, void* t0, void* t1,
-                     cudaStream_t st, const PeerOut* peers = nullptr, int64_t lp_stored = 0) {
+                     cudaStream_t st, const PeerOut* peers = nullptr, int64_t lp_stored = 0, const void** t3_only = nullptr) {
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
   // step 4 writes out[l'_slab, s1', s2', r'] -- dense, or (fused gather) a strided window of the full vector
   auto step4 = [&](const void* T3) -> int {
@@ -178,6 +178,7 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
   // 2+3 fused (one streaming pass) when the shape has an instantiation
   if (heff23_fused(h, dtype, d, clp, W1, W2, t0, t1, h->what, st)) {
     TNB_TRY(check_cuda(h, cudaGetLastError(), "heff23"));
+    if (t3_only) { *t3_only = t1; return TNB_OK; }
     return step4(t1);
   }
   {  // 2. T2[s2,r,l',s1',b] = T1 W1[a,s1,s1',b]
@@ -193,6 +194,7 @@ static int heff_core(Handle* h, int dtype, const tnb_bond_dims* d, int64_t clp, 
     TNB_TRY(contract_impl(h, dtype, 5, ea, ma, t1, 4, eb, mb, W2, 5, ec, mc, t0, nullptr, nullptr, 0, st));
   }
   // 4. out[l',s1',s2',r'] = T3 R[r,r',c]
+  if (t3_only) { *t3_only = t0; return TNB_OK; }
   return step4(t0);
 }
 
@@ -296,6 +298,46 @@ int comm_allgather(Handle* h, void* const* bufs, size_t off, size_t bytes, cudaS
     TNB_CUDA(h, cudaMemcpyAsync((char*)bufs[g] + off + (size_t)rank * bytes, src, bytes, cudaMemcpyDefault, st));
   }
   return comm_barrier(h, st);        // all slabs have landed everywhere
+}
+
+// Host-buffer form of the sharded matvec, device part: steps 1-3 once, then step 4 cut over r' into NC pieces.  Every
+// piece stores this rank's l' slab of H*phi into ALL ranks' full-vector buffers (peer stores) and, as soon as it is
+// done, its own copy of the piece starts downloading on the copy stream (a strided window of out_host, which has
+// phi's layout) while the next piece is computed: the download needs no cross-rank synchronisation, because a rank
+// downloads exactly what it computed itself.  Measured need: with 8 GPUs pulling on one host's memory a 64 MB
+// download takes 3.7-5.8 ms, a quarter of the 21 ms matvec.
+int heff_shard_fused_host_tail(Handle* h, int dtype, const tnb_bond_dims* d, int rank, int world, int64_t clp,
+                               const void* Lslab, const void* W1, const void* W2, const void* R, const void* phi,
+                               void* const* out_peers, void* t0, void* t1, void* out_host, cudaStream_t st) {
+  const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wr = d->wR;
+  const size_t es = elsize(dtype);
+  const void* T3 = nullptr;
+  TNB_TRY(heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, nullptr, t0, t1, st, nullptr, 0, &T3));
+  const int NC = cr >= 1024 ? 4 : 1;
+  for (int i = 0; i < 2 * NC + 1 && i < 16; ++i)
+    if (!h->ev[i]) TNB_CUDA(h, cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  cudaStream_t cs = h->copy_stream;
+  const int64_t rc = (cr + NC - 1) / NC;
+  const size_t col = (size_t)cl * d1 * d2;                             // elements of the full vector per unit of r'
+  for (int c = 0; c < NC; ++c) {
+    const int64_t q0 = c * rc, q1 = std::min<int64_t>(cr, q0 + rc);
+    if (q1 <= q0) continue;
+    int64_t ea[] = {cr, clp, d1, d2, wr}; int32_t ma[] = {mR, mLp, mS1p, mS2p, mC};
+    int64_t eb[] = {cr, q1 - q0, wr};     int32_t mb[] = {mR, mRp, mC};
+    int64_t sb[] = {1, cr, cr * cr};
+    int64_t ec[] = {clp, d1, d2, q1 - q0}; int32_t mc[] = {mLp, mS1p, mS2p, mRp};
+    int64_t sc[] = {1, cl, cl * d1, cl * d1 * d2};
+    void* bases[TNB_MAX_PEERS];
+    for (int g = 0; g < world; ++g) bases[g] = (char*)out_peers[g] + ((size_t)rank * clp + (size_t)q0 * col) * es;
+    TNB_TRY(contract_impl_ex(h, dtype, 5, ea, ma, T3, 3, eb, mb, (const char*)R + (size_t)q0 * cr * es, 4, ec, mc, bases[0], nullptr,
+                             nullptr, 0, st, sc, bases, world, nullptr, sb));
+    TNB_CUDA(h, cudaEventRecord(h->ev[c], st));
+    TNB_CUDA(h, cudaStreamWaitEvent(cs, h->ev[c], 0));
+    TNB_CUDA(h, cudaMemcpy2DAsync((char*)out_host + ((size_t)rank * clp + (size_t)q0 * col) * es, (size_t)cl * es,
+                                  (const char*)out_peers[rank] + ((size_t)rank * clp + (size_t)q0 * col) * es, (size_t)cl * es,
+                                  (size_t)clp * es, (size_t)d1 * d2 * (q1 - q0), cudaMemcpyDeviceToHost, cs));
+  }
+  return TNB_OK;
 }
 
 size_t heff_shard_ws_bytes(int dtype, const tnb_bond_dims* d, int64_t clp) {

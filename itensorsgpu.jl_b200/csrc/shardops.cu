@@ -14,9 +14,14 @@
 #include "tnb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace tnb {
+
+int heff_shard_fused_host_tail(Handle* h, int dtype, const tnb_bond_dims* d, int rank, int world, int64_t clp,
+                               const void* Lslab, const void* W1, const void* W2, const void* R, const void* phi,
+                               void* const* out_peers, void* t0, void* t1, void* out_host, cudaStream_t st);
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -349,9 +354,10 @@ int tnb_dmrg_bond_step_shard(tnb_handle_t h, int dtype, const tnb_bond_dims* d, 
 
 // End-to-end sharded matvec with HOST buffers (bench.py `e2e` at N > 1).  Every rank uploads only ITS r-chunk of phi
 // (1/world of the vector over PCIe), forwards it to the peers over NVLink, runs its l' slab of the matvec with the
-// all-gather fused into step 4 (after which every rank holds the full H*phi), and downloads only ITS r'-chunk of H*phi
-// (contiguous, like the upload: r is the slowest mode) -- whole job: one vector up, one vector down, everything else
-// over NVLink.  Synchronous.
+// all-gather fused into step 4 (after which every rank holds the full H*phi on the device), and downloads only ITS OWN
+// l' slab of H*phi -- a strided window of out_host (phi's layout), piece by piece over r' while the next piece is still
+// being computed (heff.cu: heff_shard_fused_host_tail).  Whole job: one vector up, one vector down, everything else over
+// NVLink.  Synchronous.
 int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* d, const void* L_slab, const void* W1,
                               const void* W2, const void* R, const void* phi_host, void* const* phi_peers,
                               void* const* out_peers, void* out_host, void* stream) {
@@ -373,7 +379,13 @@ int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* d,
   void *t0, *t1;
   TNB_TRY(ws_alloc(H, hw / 2, &t0));
   TNB_TRY(ws_alloc(H, hw / 2, &t1));
+  // TNB_E2E_TRACE=1: per-phase CUDA-event times of every call on stderr (diagnostics; adds event overhead)
+  static const bool trace = getenv("TNB_E2E_TRACE") != nullptr;
+  cudaEvent_t te[6] = {};
+  auto mark = [&](int i) { if (trace) { if (!te[i]) cudaEventCreate(&te[i]); cudaEventRecord(te[i], ST); } };
+  mark(0);
   TNB_TRY(comm_barrier(H, ST));                                       // peers are done with the previous phi / result
+  mark(1);
   if (r1 > r0) {
     char* own = (char*)phi_peers[rank] + r0 * col;
     TNB_CUDA(H, cudaMemcpyAsync(own, (const char*)phi_host + r0 * col, (r1 - r0) * col, cudaMemcpyHostToDevice, ST));
@@ -382,13 +394,24 @@ int tnb_heff_apply_shard_host(tnb_handle_t h, int dtype, const tnb_bond_dims* d,
       TNB_CUDA(H, cudaMemcpyAsync((char*)phi_peers[g] + r0 * col, own, (r1 - r0) * col, cudaMemcpyDefault, ST));
     }
   }
+  mark(2);
   TNB_TRY(comm_barrier(H, ST));                                       // the full phi is on every rank
-  TNB_TRY(heff_shard_fused_core(H, dtype, d, rank, world, clp, L_slab, W1, W2, R, phi_peers[rank], out_peers, t0, t1, ST));
-  TNB_TRY(comm_barrier(H, ST));
-  if (r1 > r0)
-    TNB_CUDA(H, cudaMemcpyAsync((char*)out_host + r0 * col, (const char*)out_peers[rank] + r0 * col, (r1 - r0) * col,
-                                cudaMemcpyDeviceToHost, ST));
-  return check_cuda(H, cudaStreamSynchronize(ST), "heff_apply_shard_host sync");
+  mark(3);
+  // the copy stream must not start before work already queued on `stream`
+  TNB_TRY(heff_shard_fused_host_tail(H, dtype, d, rank, world, clp, L_slab, W1, W2, R, phi_peers[rank], out_peers, t0, t1, out_host, ST));
+  mark(4);
+  TNB_TRY(comm_barrier(H, ST));        // every rank's slab has landed everywhere: the device copies are complete vectors
+  mark(5);
+  TNB_CUDA(H, cudaStreamSynchronize(H->copy_stream));
+  const int status = check_cuda(H, cudaStreamSynchronize(ST), "heff_apply_shard_host sync");
+  if (trace && !status) {
+    float t[5];
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], te[i], te[i + 1]);
+    fprintf(stderr, "[tnb e2e rank %d] barrier0 %.3f  h2d+forward %.3f  barrier1 %.3f  matvec (d2h overlapped) %.3f  barrier2 %.3f ms\n", rank, t[0], t[1],
+            t[2], t[3], t[4]);
+    for (auto& e : te) if (e) cudaEventDestroy(e);
+  }
+  return status;
 }
 
 }  // extern "C"

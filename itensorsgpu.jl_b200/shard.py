@@ -301,7 +301,7 @@ class ShardedHeffHost:
 
     def apply_host(self, Lslab, W1, W2, R, phi_host, out_host):
         """phi_host / out_host: pinned CPU tensors in phi's layout; only this rank's r-chunk of phi_host is read and
-        only its r'-chunk of out_host is written (``chunk_range``).  Synchronous."""
+        only its own l' slab of out_host (``slab_range(chiL, rank, world)`` of the fastest mode) is written.  Synchronous."""
         import ctypes as C
         from . import ops
         from .ops import BondDims

@@ -92,20 +92,33 @@ def _w_lanczos_and_host(rank, world, comm, cplx):
                                              sh.out_a.c_array(), sh.out_b.c_array(), 3, 1, 1e-14, C.byref(e2), C.byref(n2),
                                              tn.ops._stream()))
     errs = [abs(e1 - e2.value) / abs(e1), ot.rel_err(p2.numpy(), p1.numpy()), float(n1 != n2.value)]
-    # end-to-end host-buffer matvec: this rank's r-chunk up, this rank's r'-chunk down
+    # end-to-end host-buffer matvec: this rank's r-chunk up, this rank's own l' slab down (pieces over r')
     hh = tn.shard.ShardedHeffHost(comm, (cl, d, d, cr), dt)
     ph = torch.from_numpy(np.ascontiguousarray(phi.ravel(order="F"))).pin_memory()
     oh = torch.zeros_like(ph).pin_memory()
     want = od.heff_apply(L, W1, W2, R, phi)
-    lo, hi = hh.chunk_range()
+    lo, hi = tn.shard.slab_range(cl, rank, world)
     for rep in range(2):
         oh.zero_()
         hh.apply_host(Ls, D(W1), D(W2), D(R), ph, oh)
         got = oh.numpy().reshape((cl, d, d, cr), order="F")
-        errs.append(ot.rel_err(got[..., lo:hi], want[..., lo:hi]))
-        mask = np.ones(cr, bool); mask[lo:hi] = False
-        errs.append(float(np.abs(got[..., mask]).max()) if mask.any() else 0.0)  # nothing outside the chunk is written
+        errs.append(ot.rel_err(got[lo:hi], want[lo:hi]))
+        mask = np.ones(cl, bool); mask[lo:hi] = False
+        errs.append(float(np.abs(got[mask]).max()) if mask.any() else 0.0)       # nothing outside the slab is written
         errs.append(ot.rel_err(hh.device_result().numpy(), want))                # the device copy is the full vector
+    if not cplx:      # chiR >= 1024: step 4 in four pieces over r', each downloaded while the next is computed
+        cl2, cr2 = 4 * world, 1030
+        L2 = _rand(rng, (cl2, cl2, w), False); R2 = _rand(rng, (cr2, cr2, w), False); phi2 = _rand(rng, (cl2, d, d, cr2), False)
+        sh2 = tn.shard.ShardedSweep(comm, dt, max(cl2, cr2), d, w, min_chi=world)
+        Ls2 = sh2.to_slab(D(L2))
+        hh2 = tn.shard.ShardedHeffHost(comm, (cl2, d, d, cr2), dt)
+        ph2 = torch.from_numpy(np.ascontiguousarray(phi2.ravel(order="F"))).pin_memory()
+        oh2 = torch.zeros_like(ph2).pin_memory()
+        hh2.apply_host(Ls2, D(W1), D(W2), D(R2), ph2, oh2)
+        want2 = od.heff_apply(L2, W1, W2, R2, phi2)
+        lo2, hi2 = tn.shard.slab_range(cl2, rank, world)
+        errs.append(ot.rel_err(oh2.numpy().reshape((cl2, d, d, cr2), order="F")[lo2:hi2], want2[lo2:hi2]))
+        errs.append(ot.rel_err(hh2.device_result().numpy(), want2))
     comm.status()
     return max(errs)
 

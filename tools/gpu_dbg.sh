@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-t0=$(date +%s)
-timeout 900 python bench.py > gpurun_out/r02_bench_full.json 2> gpurun_out/r02_bench_full.err
-echo "bench full rc=$? ($(( $(date +%s) - t0 )) s)"; tail -n 3 gpurun_out/r02_bench_full.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-sweep --no-tebd --no-cpu-baseline > gpurun_out/r02_bench_under_ncu.log 2>&1
-echo "ncu rc=$?"
+timeout 200 python -m pytest "tests/test_gpu_shard_dmrg.py::test_multi_rank_suite[2]" "tests/test_gpu_shard_dmrg.py::test_multi_rank_suite[4]" -x -q -m gpu > gpurun_out/r02_suite24.log 2>&1
+echo "rc=$?"; tail -n 12 gpurun_out/r02_suite24.log
