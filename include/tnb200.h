@@ -16,7 +16,10 @@
  *     means "contract", exactly like the mode numbering at src/tensor/cudense.jl:258-283.
  *   - Caller owns every tensor buffer.  The library owns only the opaque handle
  *     (workspace arena, plan cache -- the analogue of `ContractionPlans`,
- *     src/ITensorsGPU.jl:54-55).  One handle per host thread; not thread-safe.
+ *     src/ITensorsGPU.jl:54-55).  One handle per host thread AND per device (tnb_create binds to the device that is
+ *     current when it is called); not thread-safe.  The workspace arena and the device scalar pool are reused in
+ *     stream order: issue the calls of one handle on one stream at a time (a second stream needs a second handle),
+ *     exactly like the reference's single task-local CUDA.jl stream.
  *   - All calls are asynchronous on `stream` unless they return a host scalar
  *     (documented per function).  `stream` is a cudaStream_t passed as void*.
  *   - Return value: 0 on success, a tnb_status otherwise; tnb_last_error() gives text.

@@ -178,11 +178,16 @@ class Handle:
         return int(self.lib.tnb_workspace_bytes(self.h))
 
 
-_handle = None
+_handles = {}
 
 
 def handle():
-    global _handle
-    if _handle is None:
-        _handle = Handle()
-    return _handle
+    """The library handle of the CURRENT CUDA device (one per device: its workspace arena, scratch scalars and plan
+    cache belong to that device; tnb_create binds to the device that is current when it is called).  Calls on one
+    handle must be issued from one stream at a time -- the arena is reused in stream order (include/tnb200.h)."""
+    import torch
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    h = _handles.get(dev)
+    if h is None:
+        h = _handles[dev] = Handle()
+    return h

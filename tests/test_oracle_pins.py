@@ -239,3 +239,74 @@ def test_mps_algebra_restatement(cplx):
     assert abs(omps.inner(psi, Hpsi) - omps.expect_mpo(psi, Ws)) < 1e-12 * max(1.0, abs(omps.expect_mpo(psi, Ws)))
     tr = omps.contract_mpo_mps(Ws, psi, maxdim=8)
     assert max(t.shape[2] for t in tr[:-1]) <= 8
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: MPO algebra restatements and the on-disk container (host side only)
+# ---------------------------------------------------------------------------------------------
+def test_mpo_algebra_restatement_against_dense_operators():
+    """[EXT] contract(::MPO, ::MPO) / add(::MPO, ::MPO) (test/test_cumpo.jl:133-173): the restatement reproduces the
+    dense operator algebra, with and without truncation to the exact rank, and the reference's consistency relation
+    <psi| K L |psi> == <psi| K (L psi)>."""
+    from oracle import mps as omps
+    from oracle import tensor as ot
+    rng = np.random.default_rng(21)
+    N, d = 5, 2
+    mk = lambda w, c: [(rng.standard_normal((1 if j == 0 else w, d, d, 1 if j == N - 1 else w)) +
+                        (1j * rng.standard_normal((1 if j == 0 else w, d, d, 1 if j == N - 1 else w)) if c else 0))
+                       for j in range(N)]
+    for cplx in (False, True):
+        Ks, Ls = mk(3, cplx), mk(2, cplx)
+        dK, dL = omps.mpo_to_dense(Ks), omps.mpo_to_dense(Ls)
+        assert ot.rel_err(omps.mpo_to_dense(omps.contract_mpo_mpo(Ks, Ls)), dL @ dK) < 1e-13
+        KLt = omps.contract_mpo_mpo(Ks, Ls, maxdim=6, cutoff=0.0)
+        assert max(W.shape[3] for W in KLt) <= 6
+        assert ot.rel_err(omps.mpo_to_dense(KLt), dL @ dK) < 1e-12
+        assert ot.rel_err(omps.mpo_to_dense(omps.add_mpo(Ks, Ls)), dK + dL) < 1e-13
+        psi = omps.random_mps(N, d, 4, rng, dtype=np.complex128 if cplx else np.float64)
+        lhs = omps.expect_mpo(psi, omps.contract_mpo_mpo(Ks, Ls))
+        rhs = omps.inner(psi, omps.contract_mpo_mps(Ks, omps.contract_mpo_mps(Ls, psi)))
+        assert abs(lhs - rhs) < 1e-11 * max(1.0, abs(lhs))
+
+
+def test_on_disk_container_round_trip_on_the_host(tmp_path):
+    """io.save_chain / load_chain with host-side chains (no GPU): bit-exact data, limits, extra metadata, atomic
+    replace, and rejection of foreign files."""
+    import zipfile
+    from itensorsgpu_b200 import tn
+    rng = np.random.default_rng(22)
+    ts = [rng.standard_normal((1 if j == 0 else 3, 2, 1 if j == 3 else 3)) + (1j * rng.standard_normal((1 if j == 0 else 3, 2, 1 if j == 3 else 3)) if j % 2 else 0)
+          for j in range(4)]
+    p = str(tmp_path / "psi.npz")
+    nbytes = tn.save_chain(p, tn.MPS(ts, llim=0, rlim=2), extra={"sweeps_done": 7, "energy": -1.25})
+    assert nbytes == sum(np.asarray(t).astype(np.complex128 if np.iscomplexobj(t) else np.float64).nbytes for t in ts)
+    assert not (tmp_path / "psi.npz.tmp").exists()
+    q, extra = tn.load_chain(p, device=False)
+    assert extra == {"sweeps_done": 7, "energy": -1.25} and (q.llim, q.rlim) == (0, 2)
+    assert all(np.array_equal(a, b) and a.dtype == b.dtype for a, b in zip(q.tensors, [np.asarray(t) for t in ts]))
+    with zipfile.ZipFile(p) as z:                       # the schema: meta.json + one flat column-major vector per site
+        names = set(z.namelist())
+    assert names == {"meta.json"} | {"site_%d.npy" % j for j in range(4)}
+    H = tn.MPO([rng.standard_normal((1 if j == 0 else 2, 2, 2, 1 if j == 3 else 2)) for j in range(4)])
+    tn.save_chain(p, H)
+    H2, _ = tn.load_chain(p, device=False)
+    assert isinstance(H2, tn.MPO) and all(np.array_equal(a, b) for a, b in zip(H.tensors, H2.tensors))
+    with pytest.raises(tn.TnbError):
+        tn.load_itensor(p, device=False)                # an MPO file is not an ITensor
+    bad = str(tmp_path / "bad.npz")
+    with zipfile.ZipFile(bad, "w") as z:
+        z.writestr("meta.json", '{"format": "something else"}')
+    with pytest.raises(tn.TnbError):
+        tn.load_chain(bad, device=False)
+
+
+def test_shard_layout_helpers_on_the_host():
+    """slab / chunk arithmetic of the multi-GPU sweep that needs no device"""
+    from itensorsgpu_b200 import tn
+    assert tn.shard.slab_range(4096, 3, 8) == (1536, 2048)
+    assert tn.shard.mpo_split_ranges(30, 8)[0] == (0, 4)
+    assert tn.tebd.block_range(128, 3, 8) == (48, 64)
+    import torch
+    L = torch.arange(4 * 4 * 3, dtype=torch.float64)                   # flat column-major L[l, l', a], 4 x 4 x 3
+    s = tn.shard.left_env_slab(L, 4, 3, 1, 2).numpy().reshape((4, 2, 3), order="F")
+    assert np.array_equal(s, L.numpy().reshape((4, 4, 3), order="F")[:, 2:4, :])
