@@ -87,9 +87,10 @@ size_t tnb_workspace_bytes(tnb_handle_t h);
 int tnb_plan_cache_stats(tnb_handle_t h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* autotuned);
 int tnb_plan_cache_clear(tnb_handle_t h);
 int tnb_set_autotune(tnb_handle_t h, int mode);
-/* Contraction calls per kernel family since the library was loaded: out3[0] = LDGSTS tile kernel, out3[1] = small-K
- * streaming kernel, out3[2] = TMA-staged kernel (both operands K-major; contract_tma.cu). */
-int tnb_kernel_family_counts(tnb_handle_t h, uint64_t* out3);
+/* Contraction calls per kernel family since the library was loaded: out4[0] = LDGSTS tile kernel, out4[1] = small-K
+ * streaming kernel, out4[2] = TMA-staged kernel (both operands K-major; contract_tma.cu), out4[3] = those TMA calls
+ * that split K over thread-block clusters (problems smaller than one wave of CTA slots). */
+int tnb_kernel_family_counts(tnb_handle_t h, uint64_t* out4);
 /* Upper bound (bytes) on the PAIR of temporaries of one H_eff*phi / noise term / environment update (default 40 GB;
  * 0 restores the default).  Above it the work is cut into slabs of the output bond (H_eff: independent
  * full-efficiency slabs, L taken as a strided window, result written as a strided window) or of a summed bond with

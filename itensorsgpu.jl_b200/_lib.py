@@ -154,10 +154,10 @@ class Handle:
         return dict(zip(("entries", "hits", "misses", "autotuned"), [int(x.value) for x in v]))
 
     def kernel_family_counts(self):
-        """contraction calls per kernel family: {'ldgsts', 'smallk', 'tma'}"""
-        v = (C.c_uint64 * 3)()
+        """contraction calls per kernel family: {'ldgsts', 'smallk', 'tma', 'tma_split_k'}"""
+        v = (C.c_uint64 * 4)()
         self.check(self.lib.tnb_kernel_family_counts(self.h, v))
-        return {"ldgsts": int(v[0]), "smallk": int(v[1]), "tma": int(v[2])}
+        return {"ldgsts": int(v[0]), "smallk": int(v[1]), "tma": int(v[2]), "tma_split_k": int(v[3])}
 
     def plan_cache_clear(self):
         self.check(self.lib.tnb_plan_cache_clear(self.h))

@@ -10,7 +10,7 @@ void plan_cache_drop(Handle* h);
 void plan_cache_clear(Handle* h);
 void plan_cache_stats(Handle* h, uint64_t* entries, uint64_t* hits, uint64_t* misses, uint64_t* tuned);
 void plan_cache_set_autotune(Handle* h, int mode);
-void kernel_family_counts(uint64_t out[3]);
+void kernel_family_counts(uint64_t out[4]);
 
 int set_err(Handle* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -136,9 +136,9 @@ int tnb_plan_cache_stats(tnb_handle_t h, uint64_t* entries, uint64_t* hits, uint
   return TNB_OK;
 }
 
-int tnb_kernel_family_counts(tnb_handle_t h, uint64_t* out3) {
-  if (!h || !out3) return TNB_ERR_BAD_ARG;
-  kernel_family_counts(out3);
+int tnb_kernel_family_counts(tnb_handle_t h, uint64_t* out4) {
+  if (!h || !out4) return TNB_ERR_BAD_ARG;
+  kernel_family_counts(out4);
   return TNB_OK;
 }
 

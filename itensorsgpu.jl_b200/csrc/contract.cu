@@ -33,6 +33,7 @@ int launch_smallk_c128(Handle* h, GemmParams& p, cudaStream_t st);
 bool tma_eligible(const GemmParams& p, int dtype, bool small);
 int launch_tma(Handle* h, int dtype, GemmParams& p, bool small, cudaStream_t st);
 bool tma_would_split(Handle* h, const GemmParams& p, int dtype, bool small);
+uint64_t tma_split_launches();
 
 // ------------------------------------------------------------------------------------
 // Plan cache (the analogue of the reference's `ContractionPlans` dictionary + cuTENSOR autotune,
@@ -145,9 +146,10 @@ static Variant choose_variant(Handle* h, int dtype, const GemmParams& p) {
   return v;
 }
 
-// launches per kernel family since load: [0] LDGSTS tile kernel, [1] small-K streaming kernel, [2] TMA kernel calls
+// calls per kernel family since load: [0] LDGSTS tile kernel, [1] small-K streaming kernel, [2] TMA kernel,
+// [3] TMA calls that split K over clusters
 static uint64_t g_family[3] = {0, 0, 0};
-void kernel_family_counts(uint64_t out[3]) { for (int i = 0; i < 3; ++i) out[i] = g_family[i]; }
+void kernel_family_counts(uint64_t out[4]) { for (int i = 0; i < 3; ++i) out[i] = g_family[i]; out[3] = tma_split_launches(); }
 
 static int launch_variant(Handle* h, int dtype, GemmParams& p, const Variant& v, cudaStream_t st) {
   const bool cplx = dtype == TNB_C128;
@@ -165,9 +167,9 @@ static int launch_planned(Handle* h, int dtype, GemmParams& p, cudaStream_t st) 
 
 // One-shot autotune of a new shape: time the candidate variants on the caller's operands (beta = 0 only: the call is
 // then idempotent) and keep the fastest.  Candidates never differ in the bits they produce:
-//   * TMA-eligible shape whose tail wave is not split: TMA-staged kernel vs LDGSTS kernel, same tile (the two families
+//   * TMA-eligible shape that does not split K over clusters: TMA-staged kernel vs LDGSTS kernel, same tile (the two families
 //     share the k order; measured at chi = 4096: step 1 is 2.5% faster through TMA, step 4 2.8% faster through LDGSTS);
-//   * TMA-eligible shape WITH a split tail: never tuned (the split changes the summation order and is a function of
+//   * TMA-eligible shape that DOES split K (sub-wave problems): never tuned (the split changes the summation order and is a function of
 //     the shape alone);
 //   * other shapes: large vs small tile of the LDGSTS kernel.
 // Returns with C holding the result.

@@ -18,10 +18,11 @@
 //   * mbarrier hand-off both ways: the producer arms full[s] with the byte count and consumers wait on its phase; each
 //     warp releases a stage on empty[s] once its DMMAs have consumed the last fragment, and the producer refills the
 //     slot two k-tiles ahead.  There is no CTA-wide barrier in the main loop.
-//   * Tail-wave split-K over thread-block clusters: when the last wave of tiles would leave most of the 296 CTA slots
-//     idle (H_eff step 4 of an 8-way shard: 1024 tiles = 3.46 waves), the tiles of that wave are launched as clusters
-//     of 2 or 4 CTAs that each take a K range and reduce through distributed shared memory in a fixed order
-//     (deterministic; decided from the shape alone, so every rank of a sharded sweep sums in the same order).
+//   * Split-K over thread-block clusters for problems smaller than one wave of the 296 CTA slots (chi = 256-512 and edge
+//     bonds): the tiles are launched as clusters of 2 or 4 CTAs that each take a K range and reduce through distributed
+//     shared memory in a fixed order (deterministic; decided from the shape alone, so every rank of a sharded sweep
+//     sums in the same order).  Splitting the partial LAST wave of a large problem was measured and rejected (see
+//     tail_split below).
 //
 // tcgen05 / TMEM has no FP64 kind: the math stays warp-level mma.sync.m8n8k4.f64 = DMMA.8x8x4.
 #include <cuda.h>
@@ -494,13 +495,22 @@ static int make_map(Handle* h, CUtensorMap* map, const Group& gk, const Group& g
   return TNB_OK;
 }
 
-// tail wave: when the last partial wave wastes more than 10% of the launch, its tiles run as clusters of 2 or 4 CTAs
-// that split K (a function of the shape only: every rank / every run sums in the same order)
+// Split-K over clusters for problems SMALLER THAN ONE WAVE of CTA slots (chi = 256-512 bonds, edge bonds): their tiles
+// run as clusters of 2 or 4 CTAs that split K (a function of the shape only: every rank / every run sums in the same
+// order).  Larger problems are never split: measured on the step-4 GEMM of an 8-way shard (1024 tiles on 296 slots =
+// 3.46 waves) the un-split launch is 1.5% FASTER (10.55 vs 10.71 ms, profiles/r02_ab_tail_split_step4_n8_shape.jsonl)
+// -- the CTAs of a partial last wave have their SM's DMMA pipe to themselves and finish in about half the time, so
+// wave quantisation costs far less than the tile count suggests.  TNB_SPLITK=tail restores the tail-wave split.
+static uint64_t g_split_launches = 0;
+uint64_t tma_split_launches() { return g_split_launches; }
+
 static int tail_split(Handle* h, const GemmParams& p, long long tiles, int KT) {
   static const bool nosplit = getenv("TNB_SPLITK") && !strcmp(getenv("TNB_SPLITK"), "off");
+  static const bool tailsplit = getenv("TNB_SPLITK") && !strcmp(getenv("TNB_SPLITK"), "tail");
   const long long slots = 2LL * h->num_sms;
   const long long fullw = tiles / slots, rem = tiles - fullw * slots;
   if (nosplit || rem == 0 || p.lowerOnly) return 1;
+  if (fullw > 0 && !tailsplit) return 1;
   const double eff = (double)tiles / (double)((fullw + 1) * slots);
   if (eff >= 0.9) return 1;
   if (rem * 4 <= slots && KT >= 32) return 4;
@@ -555,6 +565,7 @@ static int launch_tma_cfg(Handle* h, GemmParams& p, cudaStream_t st) {
     return TNB_OK;
   };
   if (ks == 1) return launch(0, tiles, 1);
+  g_split_launches++;
   TNB_TRY(launch(0, fullw * slots, 1));
   return launch(fullw * slots, rem, ks);
 }

@@ -52,23 +52,23 @@ def test_tma_contraction_cases(case, cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-@pytest.mark.parametrize("K,launches", [(1024, 2), (256 + 16 * 7, 2), (64, 1)])
-def test_tma_tail_wave_split_k(K, launches, cplx):
-    """304 (complex: 608 of the 64x64) tiles on 296 CTA slots: one full wave + a tail of 8 (16) tiles, which runs as
-    clusters of 4 (K >= 512) or 2 CTAs splitting K and reducing through distributed shared memory; K = 64 is too
-    short to split.  Deterministic: two runs are bit-identical."""
+@pytest.mark.parametrize("mt,nt,K,split", [(4, 16, 1024, True), (2, 8, 1024, True), (2, 8, 512 + 16 * 7, True), (2, 8, 64, False),
+                                           (19, 16, 1024, False)])
+def test_tma_split_k_below_one_wave(mt, nt, K, split, cplx):
+    """Problems smaller than one wave of the 296 CTA slots run as clusters of 2 (128 small tiles) or 4 (32 small tiles)
+    CTAs that split K and reduce through distributed shared memory; K = 64 is too short to split and 304 tiles (more
+    than a wave) are never split (measured: no gain, profiles/r02_ab_tail_split_step4_n8_shape.jsonl).  Deterministic:
+    two runs are bit-identical."""
     from itensorsgpu_b200 import tn
     h = tn.handle()
     rng = np.random.default_rng(92)
-    M, N = 64 * 19, 128 * 16
-    if cplx:
-        N = 64 * 32
+    M, N = 64 * mt, (64 if cplx else 128) * nt
     A = rand(rng, (K, M), cplx); B = rand(rng, (K, N), cplx)
     dA, dB = dev(A), dev(B)
-    h.plan_cache_clear()
-    l0, t0 = h.launches, _tma_calls(h)
+    c0 = h.kernel_family_counts()
     out1 = tn.ops.contract(dA, ("k", "m"), dB, ("k", "n"))[0].numpy()
-    assert h.launches - l0 == launches and _tma_calls(h) == t0 + 1
+    c1 = h.kernel_family_counts()
+    assert c1["tma"] == c0["tma"] + 1 and (c1["tma_split_k"] - c0["tma_split_k"] == (1 if split else 0))
     out2 = tn.ops.contract(dA, ("k", "m"), dB, ("k", "n"))[0].numpy()
     assert np.array_equal(out1, out2)
     assert ot.rel_err(out1, A.T @ B) < 1e-12
