@@ -314,7 +314,7 @@ int heff_shard_fused_host_tail(Handle* h, int dtype, const tnb_bond_dims* d, int
   const void* T3 = nullptr;
   TNB_TRY(heff_core(h, dtype, d, clp, Lslab, W1, W2, R, phi, nullptr, t0, t1, st, nullptr, 0, &T3));
   const int NC = cr >= 1024 ? 4 : 1;
-  for (int i = 0; i < 2 * NC + 1 && i < 16; ++i)
+  for (int i = 0; i < 2 * NC + 1 && i < 40; ++i)
     if (!h->ev[i]) TNB_CUDA(h, cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
   cudaStream_t cs = h->copy_stream;
   const int64_t rc = (cr + NC - 1) / NC;
@@ -711,7 +711,11 @@ static int heff_host_pipelined(Handle* h, int dtype, const tnb_bond_dims* d, con
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2, wl = d->wL, wm = d->wM, wr = d->wR;
   const size_t es = elsize(dtype);
   const size_t nb = (size_t)cl * cr * d1 * d2 * es;
-  const int NC = (cr >= 1024 && heff_nchunks(dtype, d) == 1) ? 4 : 1;
+  // chunks over r / r': the exposed copy time is one chunk each way, but smaller GEMM chunks lose efficiency -- measured at
+  // chi = 4096 (e2e TFLOP/s): 4 chunks 33.59, 8 chunks 32.77, 16 chunks 31.38 (device-resident: 34.87).  TNB_HOST_CHUNKS
+  // overrides the default of 4.
+  static const int nc_env = getenv("TNB_HOST_CHUNKS") ? std::max(1, std::min(16, atoi(getenv("TNB_HOST_CHUNKS")))) : 4;
+  const int NC = (cr >= 1024 && heff_nchunks(dtype, d) == 1) ? nc_env : 1;
   if (NC == 1) {
     TNB_CUDA(h, cudaMemcpyAsync(dphi, phi_host, nb, cudaMemcpyHostToDevice, st));
     TNB_TRY(heff_apply_any(h, dtype, d, L, W1, W2, R, dphi, dout, t0, t1, st));

@@ -80,7 +80,7 @@ struct Handle {
   double* partials = nullptr;   // per-block partial sums for reductions (8192 doubles)
   unsigned* counter = nullptr;  // last-block-done ticket (self-resetting)
   void* what = nullptr;         // combined two-site MPO matrix of the fused H_eff step 2+3 (64 KB)
-  cudaEvent_t ev[16] = {};      // chunk hand-over events of the pipelined host-buffer H_eff (created on first use)
+  cudaEvent_t ev[40] = {};      // chunk hand-over events of the pipelined host-buffer H_eff (created on first use)
   Comm comm;                    // peer group (tnb_comm_init)
 };
 constexpr int RED_MAX_BLOCKS = 1024;
