@@ -340,6 +340,28 @@ int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* dims, int
                        double cutoff, double noise, int krylovdim, int maxiter,
                        double* energy, int64_t* n_keep, double* truncerr, void* stream);
 
+/* One full two-site DMRG sweep (left-to-right, then right-to-left: 2(nsites-1) bond steps) with the host control flow
+ * inside the library ([EXT] the body of ITensors' sweep loop in src/mps/dmrg.jl: sweepnext / position! / eigsolve /
+ * replacebond!; reference call sites examples/dmrg.jl:25, test/dmrg.jl:27,75).  The orthogonality centre must be at
+ * site 0 on entry and is there again on return.
+ *   chi[0..nsites]   bond dimensions (chi[0] = chi[nsites] = 1), UPDATED in place
+ *   d[j], w[t]       site dimensions, MPO bond dimensions (w[0] = w[nsites] = 1)
+ *   A[j], capA[j]    site tensors A[chi[j], d[j], chi[j+1]] in buffers of capA[j] elements; a bond step needs room for
+ *                    kmax = min(r, maxdim) (tnb_factorize_bond's capacity rule) on both of its sites
+ *   W[j]             MPO tensors W[w[j], d[j], d[j], w[j+1]]
+ *   env[t], capE[t]  one environment buffer per boundary t = 0..nsites (boundary t is left of site t), capE[t] >=
+ *                    chi_max[t]^2 * w[t] elements: it holds the LEFT environment of the boundary while the centre is
+ *                    right of it and the RIGHT environment otherwise.  build_right_envs != 0 builds the right
+ *                    environments of boundaries 2..nsites-1 first ([EXT] position!(PH, psi, 1)); with 0 they must be
+ *                    the ones a previous call left behind.
+ *   bond_energies / bond_truncerrs (optional, 2(nsites-1) doubles each): per bond step, in sweep order.
+ * Synchronises. */
+int tnb_dmrg_sweep(tnb_handle_t h, int dtype, int32_t nsites, int64_t* chi, const int32_t* d, const int32_t* w,
+                   void* const* A, const int64_t* capA, const void* const* W, void* const* env, const int64_t* capE,
+                   int build_right_envs, int64_t maxdim, int64_t mindim, double cutoff, double noise, int which_decomp,
+                   int krylovdim, int maxiter, double* energy, double* maxerr, double* bond_energies,
+                   double* bond_truncerrs, void* stream);
+
 /* theta[l,s1',s2',r] <- sum G[s1',s2',s1,s2] A1[l,s1,k] A2[k,s2,r]  then left-orthogonal
  * split with truncation ([EXT] apply / product(o, psi); examples/gate_evolution.jl:46).  A1 / A2 capacities as for
  * tnb_dmrg_bond_step with ortho left (cutoff > 1e-12 selects the eigen branch: kmax = min(chiL*d1, maxdim)). */

@@ -96,6 +96,8 @@ SIGNATURES = {
                                   _pdbl, _vp]),
     "tnb_dmrg_bond_step": (_int, [_vp, _int, _pbd, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _i64, _dbl, _dbl,
                                   _int, _int, _pdbl, _pi64, _pdbl, _vp]),
+    "tnb_dmrg_sweep": (_int, [_vp, _int, _i32, _pi64, _pi32, _pi32, C.POINTER(_vp), _pi64, C.POINTER(_vp), C.POINTER(_vp), _pi64,
+                              _int, _i64, _i64, _dbl, _dbl, _int, _int, _int, _pdbl, _pdbl, _pdbl, _pdbl, _vp]),
     "tnb_tebd_apply_gate": (_int, [_vp, _int, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _dbl, _pi64,
                                    _pdbl, _vp]),
     "tnb_tebd_gate_bform": (_int, [_vp, _int, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _vp,

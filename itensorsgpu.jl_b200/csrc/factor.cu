@@ -373,6 +373,79 @@ int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* d, int64_
   return check_cuda(H, cudaStreamSynchronize(ST), "dmrg_bond_step sync");
 }
 
+// One full two-site DMRG sweep with the host control flow in C++ ([EXT] the body of ITensors' `for sw = 1:nsweep(sweeps)`
+// loop in src/mps/dmrg.jl -- sweepnext, position!, eigsolve, replacebond! -- reached by the reference at
+// examples/dmrg.jl:25 and test/dmrg.jl:27,75).  Boundary t (t = 0..N) sits left of site t:
+// env[t] holds the LEFT environment of boundary t while the orthogonality centre is at or right of it, and the RIGHT
+// environment otherwise -- exactly one of the two is ever alive, so one buffer per boundary is enough.
+int tnb_dmrg_sweep(tnb_handle_t h, int dtype, int32_t nsites, int64_t* chi, const int32_t* d, const int32_t* w,
+                   void* const* A, const int64_t* capA, const void* const* W, void* const* env, const int64_t* capE,
+                   int build_right_envs, int64_t maxdim, int64_t mindim, double cutoff, double noise, int which_decomp,
+                   int krylovdim, int maxiter, double* energy, double* maxerr, double* bond_energies,
+                   double* bond_truncerrs, void* stream) {
+  if (!h) return TNB_ERR_BAD_ARG;
+  if (!chi || !d || !w || !A || !capA || !W || !env || !capE) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_sweep: null pointer");
+  if (nsites < 2) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_sweep: needs at least 2 sites");
+  if (maxdim < 1) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_sweep: maxdim < 1");
+  const int N = nsites;
+  const size_t es = elsize(dtype);
+  if (chi[0] != 1 || chi[N] != 1 || w[0] != 1 || w[N] != 1) return set_err(H, TNB_ERR_DIM_MISMATCH, "dmrg_sweep: open boundary bonds must have dimension 1");
+  for (int j = 0; j < N; ++j) {
+    if (!A[j] || !W[j]) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_sweep: null site tensor %d", j);
+    if (capA[j] < chi[j] * d[j] * chi[j + 1]) return set_err(H, TNB_ERR_DIM_MISMATCH, "dmrg_sweep: site buffer %d too small", j);
+  }
+  for (int t = 0; t <= N; ++t)
+    if (!env[t] || capE[t] < 1) return set_err(H, TNB_ERR_BAD_ARG, "dmrg_sweep: null environment buffer %d", t);
+  {  // trivial boundary environments
+    double one[2] = {1.0, 0.0};
+    TNB_CUDA(H, cudaMemcpyAsync(env[0], one, es, cudaMemcpyHostToDevice, ST));
+    TNB_CUDA(H, cudaMemcpyAsync(env[N], one, es, cudaMemcpyHostToDevice, ST));
+    TNB_CUDA(H, cudaStreamSynchronize(ST));
+  }
+  auto need_env = [&](int t) -> int {
+    if (capE[t] < chi[t] * chi[t] * (int64_t)w[t]) return set_err(H, TNB_ERR_DIM_MISMATCH, "dmrg_sweep: environment buffer %d too small (%lld < %lld)", t, (long long)capE[t], (long long)(chi[t] * chi[t] * w[t]));
+    return TNB_OK;
+  };
+  if (build_right_envs) {
+    for (int j = N - 1; j >= 2; --j) {            // R_j covers sites >= j
+      TNB_TRY(need_env(j));
+      TNB_TRY(tnb_env_update_right(h, dtype, chi[j], chi[j + 1], d[j], w[j], w[j + 1], env[j + 1], A[j], W[j], env[j], stream));
+    }
+  }
+  const bool eigen_rule = which_decomp == TNB_DECOMP_EIGEN || (which_decomp == TNB_DECOMP_AUTO && (noise > 0 || cutoff > 1e-12));
+  double worst = 0.0, e = 0.0;
+  int step = 0;
+  for (int half = 0; half < 2; ++half) {
+    for (int i = 0; i < N - 1; ++i, ++step) {
+      const int b = half == 0 ? i : N - 2 - i;
+      const int ortho = half == 0 ? TNB_ORTHO_LEFT : TNB_ORTHO_RIGHT;
+      tnb_bond_dims bd;
+      bd.chiL = chi[b]; bd.chiR = chi[b + 2]; bd.d1 = d[b]; bd.d2 = d[b + 1]; bd.wL = w[b]; bd.wM = w[b + 1]; bd.wR = w[b + 2];
+      const int64_t m = bd.chiL * bd.d1, n = (int64_t)bd.d2 * bd.chiR;
+      const int64_t r = eigen_rule ? (ortho == TNB_ORTHO_LEFT ? m : n) : std::min(m, n);
+      const int64_t kmax = std::max<int64_t>(1, std::min(r, maxdim));
+      if (capA[b] < m * kmax || capA[b + 1] < kmax * n)
+        return set_err(H, TNB_ERR_DIM_MISMATCH, "dmrg_sweep: site buffers of bond %d cannot hold a bond dimension of %lld", b, (long long)kmax);
+      int64_t nk = 0;
+      double err = 0.0;
+      TNB_TRY(tnb_dmrg_bond_step(h, dtype, &bd, chi[b + 1], env[b], W[b], W[b + 1], env[b + 2], A[b], A[b + 1], ortho, which_decomp, maxdim,
+                                 mindim, cutoff, noise, krylovdim, maxiter, &e, &nk, &err, stream));
+      chi[b + 1] = nk;
+      TNB_TRY(need_env(b + 1));
+      if (ortho == TNB_ORTHO_LEFT)
+        TNB_TRY(tnb_env_update_left(h, dtype, chi[b], chi[b + 1], d[b], w[b], w[b + 1], env[b], A[b], W[b], env[b + 1], stream));
+      else
+        TNB_TRY(tnb_env_update_right(h, dtype, chi[b + 1], chi[b + 2], d[b + 1], w[b + 1], w[b + 2], env[b + 2], A[b + 1], W[b + 1], env[b + 1], stream));
+      worst = std::max(worst, err);
+      if (bond_energies) bond_energies[step] = e;
+      if (bond_truncerrs) bond_truncerrs[step] = err;
+    }
+  }
+  if (energy) *energy = e;
+  if (maxerr) *maxerr = worst;
+  return check_cuda(H, cudaStreamSynchronize(ST), "dmrg_sweep sync");
+}
+
 int tnb_tebd_apply_gate(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, int64_t chiR, int32_t d1, int32_t d2,
                         const void* G, void* A1, void* A2, int64_t maxdim, int64_t mindim, double cutoff,
                         int64_t* n_keep, double* truncerr, void* stream) {

@@ -377,8 +377,57 @@ class _EnvCache:
         return self.dev[j]
 
 
+def _dmrg_native(ts, Ws, dt, sweeps, krylovdim, maxiter, which_decomp, outputlevel, observer, checkpoint):
+    """The sweep loop inside the library (``tnb_dmrg_sweep``): Python only allocates the buffers -- site tensors and one
+    environment per boundary at their maxdim capacity -- and makes ONE C call per sweep."""
+    import ctypes as C
+    h = _lib.handle()
+    N = len(ts)
+    dev = ts[0].data.device
+    d = [t.dims[1] for t in ts]
+    w = [W.dims[0] for W in Ws] + [Ws[-1].dims[3]]
+    chi = [ts[0].dims[0]] + [t.dims[2] for t in ts]
+    mx = max(max(sweeps.maxdim), max(chi))
+    cap = [1] + [mx] * (N - 1) + [1]                       # the eigen branch may keep up to maxdim on any inner bond
+    A, E = [], []
+    for j in range(N):
+        buf = torch.empty(cap[j] * d[j] * cap[j + 1], dtype=dt, device=dev)
+        buf[: ts[j].size].copy_(ts[j].data)
+        A.append(buf)
+    for t in range(N + 1):
+        E.append(torch.empty(max(1, cap[t] * cap[t] * w[t]), dtype=dt, device=dev))
+    vp = lambda xs: (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    i64 = lambda xs: (C.c_int64 * len(xs))(*[int(x) for x in xs])
+    i32 = lambda xs: (C.c_int32 * len(xs))(*[int(x) for x in xs])
+    cchi = i64(chi)
+    pA, pW, pE = vp(A), vp([W.data for W in Ws]), vp(E)
+    capA, capE = i64([a.numel() for a in A]), i64([e.numel() for e in E])
+    nb = 2 * (N - 1)
+    energy = None
+    for sw in range(sweeps.nsweep):
+        e, merr = C.c_double(0.0), C.c_double(0.0)
+        be, bt = (C.c_double * nb)(), (C.c_double * nb)()
+        h.check(h.lib.tnb_dmrg_sweep(h.h, ops._dt(A[0]), N, cchi, i32(d), i32(w), pA, capA, pW, pE, capE, 1 if sw == 0 else 0,
+                                     sweeps.maxdim[sw], sweeps.mindim[sw], sweeps.cutoff[sw], sweeps.noise[sw],
+                                     ops._DECOMP[which_decomp], krylovdim, maxiter, C.byref(e), C.byref(merr), be, bt,
+                                     ops._stream()))
+        energy = e.value
+        if observer:                                        # per-bond data of the finished sweep, in sweep order
+            for i in range(nb):
+                b, o = (i, "left") if i < N - 1 else (nb - 1 - i, "right")
+                observer(sw, b, o, be[i], bt[i])
+        if outputlevel > 0:
+            print("After sweep %d energy=%.12f maxlinkdim=%d maxerr=%.2E" % (sw + 1, energy, max(cchi[1:N]), merr.value))
+        if checkpoint:
+            from .io import save_chain
+            cur = [DTensor(A[j][: cchi[j] * d[j] * cchi[j + 1]], (cchi[j], d[j], cchi[j + 1])) for j in range(N)]
+            save_chain(checkpoint, MPS(cur, llim=-1, rlim=1), extra={"sweeps_done": sw + 1, "energy": energy})
+    out = [DTensor(A[j][: cchi[j] * d[j] * cchi[j + 1]].clone(), (cchi[j], d[j], cchi[j + 1])) for j in range(N)]
+    return energy, MPS(out, llim=-1, rlim=1)
+
+
 def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel=0, observer=None, env_store="device",
-         comm=None, shard_min_chi=256, verify_ranks=False, checkpoint=None):
+         comm=None, shard_min_chi=256, verify_ranks=False, checkpoint=None, driver="python"):
     """``energy, psi = dmrg(H, psi0, sweeps)`` ([EXT] ITensors 0.2 two-site DMRG; reference call sites
     ``examples/dmrg.jl:25``, ``test/dmrg.jl:27,75``).  Per bond: ONE fused C call (phi = A1*A2, Lanczos with
     krylovdim matvecs, optional noise term, truncated factorization) plus one environment update.
@@ -390,6 +439,11 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
     the factorization is replicated.  Energies and the MPS are bit-identical on every rank and equal to the 1-GPU
     sweep's up to the summation order of the sharded GEMMs (tests: 1e-12).  ``verify_ranks`` cross-checks
     (energy, n_keep) over the ranks after every bond.
+
+    ``driver="native"``: the whole sweep loop runs inside the library (``tnb_dmrg_sweep``, one C call per sweep; site
+    tensors and one environment per boundary are allocated once at their maxdim capacity).  Same kernels in the same
+    order, so energies are bit-identical to the Python loop; the observer is then called after each sweep with that
+    sweep's per-bond data.  Not combined with ``comm`` / ``env_store="host"``.
 
     ``checkpoint`` (a path): after every sweep the MPS (orthogonality centre back at site 0) is written with
     ``io.save_chain`` together with {"sweeps_done", "energy"}; ``load_chain`` + ``dmrg`` with the remaining sweeps
@@ -405,6 +459,12 @@ def dmrg(H, psi0, sweeps, krylovdim=3, maxiter=1, which_decomp=None, outputlevel
     dt = torch.complex128 if any(t.dtype == torch.complex128 for t in ts + list(Ws)) else torch.float64
     ts = [t.astype(dt) for t in ts]
     Ws = [w.astype(dt) for w in Ws]
+    if driver not in ("python", "native"):
+        raise _lib.TnbError(1, "dmrg: driver must be 'python' or 'native'")
+    if driver == "native":
+        if (comm is not None and comm.world > 1) or env_store != "device":
+            raise _lib.TnbError(3, "dmrg: driver='native' runs on one GPU with the environments on the device")
+        return _dmrg_native(ts, Ws, dt, sweeps, krylovdim, maxiter, which_decomp, outputlevel, observer, checkpoint)
     one = DTensor(torch.ones(1, dtype=dt, device="cuda"), (1, 1, 1))
     sh = None
     if comm is not None and comm.world > 1:

@@ -352,4 +352,21 @@ function dmrg_bond_step_shard!(Lslab, W1, W2, R, b1::CuVector{ElT}, b2::CuVector
   return e[], Int(nk[]), err[]
 end
 
+# ---- one full sweep of dmrg(): 2(N-1) bond steps + environment updates, host loop inside the library
+# A, W, env: Vector{CuArray} (site tensors / MPO tensors / one environment buffer per boundary 0..N), chi updated in place
+function dmrg_sweep!(A::Vector{<:CuArray{ElT}}, W::Vector{<:CuArray{ElT}}, env::Vector{<:CuArray{ElT}}, chi::Vector{Int64},
+                     d::Vector{Int32}, w::Vector{Int32}; build_right_envs::Bool, maxdim::Int, mindim::Int=1, cutoff::Float64=0.0,
+                     noise::Float64=0.0, which_decomp::Int=0, krylovdim::Int=3, maxiter::Int=1) where {ElT}
+  N = length(A)
+  e, merr = Ref{Float64}(0.0), Ref{Float64}(0.0)
+  be, bt = zeros(Float64, 2(N - 1)), zeros(Float64, 2(N - 1))
+  check(ccall((:tnb_dmrg_sweep, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}},
+               Ptr{Int64}, Cint, Int64, Int64, Float64, Float64, Cint, Cint, Cint, Ref{Float64}, Ref{Float64}, Ptr{Float64},
+               Ptr{Float64}, Ptr{Cvoid}),
+              handle(), dtype(ElT), N, chi, d, w, ptr.(A), Int64.(length.(A)), ptr.(W), ptr.(env), Int64.(length.(env)),
+              build_right_envs ? 1 : 0, maxdim, mindim, cutoff, noise, which_decomp, krylovdim, maxiter, e, merr, be, bt, stream()))
+  return e[], merr[], be, bt
+end
+
 end # module

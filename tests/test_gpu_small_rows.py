@@ -188,3 +188,24 @@ def test_on_disk_round_trip_and_dmrg_resume(tmp_path):
     assert extra["sweeps_done"] == 2 and extra["energy"] == e_half and psi_ck.llim == -1 and psi_ck.rlim == 1
     e_res, _ = tn.dmrg(H, psi_ck, tn.Sweeps(2, maxdim=kw["maxdim"][2:], cutoff=1e-12, noise=kw["noise"][2:]))
     assert e_res == e_full
+
+
+# ---------------------------------------------------------------- native sweep driver (tnb_dmrg_sweep)
+@pytest.mark.parametrize("cplx", [False, True])
+def test_native_sweep_driver_matches_python_loop(cplx):
+    """The C++ sweep loop issues the same bond steps and environment updates as the Python loop: every bond energy, the
+    truncation errors, the bond dimensions and the final state are bit-identical (svd rule, eigen + noise rule, growing
+    maxdim, mindim; real and complex)."""
+    from itensorsgpu_b200 import tn
+    N = 10
+    H = tn.cu(tn.heisenberg_mpo(N, 0.5))
+    psi0 = tn.randomCuMPS(N, 2, chi=4, seed=21, dtype=np.complex128 if cplx else np.float64)
+    for kw in (dict(maxdim=[4, 8, 16], cutoff=0.0), dict(maxdim=[6, 12, 20], mindim=[1, 4], cutoff=1e-10, noise=[1e-6, 1e-8, 0.0])):
+        a, b = [], []
+        e1, p1 = tn.dmrg(H, psi0, tn.Sweeps(3, **kw), observer=lambda s, bb, o, e, err: a.append((s, bb, o, e, err)))
+        e2, p2 = tn.dmrg(H, psi0, tn.Sweeps(3, **kw), driver="native", observer=lambda s, bb, o, e, err: b.append((s, bb, o, e, err)))
+        assert a == b and e1 == e2
+        assert [t.dims for t in p1.tensors] == [t.dims for t in p2.tensors]
+        assert all(np.array_equal(x.numpy(), y.numpy()) for x, y in zip(p1.tensors, p2.tensors))
+    with pytest.raises(tn.TnbError):
+        tn.dmrg(H, psi0, tn.Sweeps(1, maxdim=4), driver="native", env_store="host")
