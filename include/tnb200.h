@@ -102,6 +102,38 @@ size_t tnb_get_workspace_limit(tnb_handle_t h);
 /* Number of kernels this library has launched through the handle (bench `gpu_launches`). */
 uint64_t tnb_launch_count(tnb_handle_t h);
 
+/* Dry run of tnb_contract's planner: how the contraction is matricised and which kernel family / tile it maps to.
+ * Pure host logic -- needs neither a handle nor a GPU (the `-m "not gpu"` tests drive the planner through it and
+ * replay the address arithmetic below against the CPU oracle).  The analogue on the reference side is the host part
+ * of _contract! (src/tensor/cudense.jl:255-294: mode numbering, the string key, the descriptor set-up).
+ *   C[sum_i dm_i c_stride_m[i] + sum_j dn_j c_stride_n[j]]
+ *       = sum_k A[sum_i dm_i a_stride_m[i] + sum_l dk_l a_stride_k[l]] * B[sum_j dn_j b_stride_n[j] + sum_l dk_l b_stride_k[l]]
+ * where (dm_i) are the mixed-radix digits of m in [0, M) over ext_m (ext_m[0] fastest), likewise n and k.
+ * Extent-1 modes are dropped and modes adjacent in both carrying tensors are fused.  Operands are taken as dense
+ * column-major with 16-byte aligned base pointers.  num_sms <= 0 means 148 (B200). */
+#define TNB_PLAN_MAX_MODES 12
+typedef struct {
+  int64_t M, N, K;
+  int32_t n_m, n_n, n_k;          /* merged modes per group */
+  int32_t family;                 /* 0 = LDGSTS tile kernel, 1 = small-K streaming kernel, 2 = TMA-staged tile kernel
+                                     (shape eligible: both operands K-major, <= 5-D boxes; the run-time autotune may still
+                                     prefer family 0 for a given shape) */
+  int64_t ext_m[TNB_PLAN_MAX_MODES], a_stride_m[TNB_PLAN_MAX_MODES], c_stride_m[TNB_PLAN_MAX_MODES];
+  int64_t ext_n[TNB_PLAN_MAX_MODES], b_stride_n[TNB_PLAN_MAX_MODES], c_stride_n[TNB_PLAN_MAX_MODES];
+  int64_t ext_k[TNB_PLAN_MAX_MODES], a_stride_k[TNB_PLAN_MAX_MODES], b_stride_k[TNB_PLAN_MAX_MODES];
+  int32_t a_k_major, b_k_major;   /* staging direction of each operand's tiles (1 = along K) */
+  int32_t a_vec, b_vec;           /* elements per asynchronous copy (2 = 16-byte copies of f64) */
+  int32_t tile_m, tile_n, tile_k;
+  int32_t herm_upper;             /* 1 if TNB_HERM_UPPER is honoured (upper-triangle tiles only) */
+  int64_t tiles;                  /* CTAs of the launch */
+  double waves;                   /* tiles / (2 CTA slots x num_sms) */
+} tnb_plan_desc;
+int tnb_plan_describe(int dtype,
+                      int nA, const int64_t* extA, const int32_t* modeA,
+                      int nB, const int64_t* extB, const int32_t* modeB,
+                      int nC, const int64_t* extC, const int32_t* modeC,
+                      int flags, int num_sms, tnb_plan_desc* out, char* err, size_t errlen);
+
 /* ------------------------------------------------------------------ tier 1: primitives - */
 
 /* C[modeC] <- alpha * sum_{shared} A[modeA] * B[modeB] + beta * C[modeC]

@@ -34,6 +34,19 @@ class BondDims(C.Structure):
                 ("wL", C.c_int32), ("wM", C.c_int32), ("wR", C.c_int32)]
 
 
+class PlanDesc(C.Structure):
+    """tnb_plan_desc (include/tnb200.h): the planner's matricisation of one contraction."""
+    _A = C.c_int64 * 12
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("n_m", C.c_int32), ("n_n", C.c_int32), ("n_k", C.c_int32), ("family", C.c_int32),
+                ("ext_m", _A), ("a_stride_m", _A), ("c_stride_m", _A),
+                ("ext_n", _A), ("b_stride_n", _A), ("c_stride_n", _A),
+                ("ext_k", _A), ("a_stride_k", _A), ("b_stride_k", _A),
+                ("a_k_major", C.c_int32), ("b_k_major", C.c_int32), ("a_vec", C.c_int32), ("b_vec", C.c_int32),
+                ("tile_m", C.c_int32), ("tile_n", C.c_int32), ("tile_k", C.c_int32), ("herm_upper", C.c_int32),
+                ("tiles", C.c_int64), ("waves", C.c_double)]
+
+
 _vp, _i64, _i32, _int, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_double
 _pi64, _pi32, _pdbl, _pint = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int)
 _pbd = C.POINTER(BondDims)
@@ -47,6 +60,8 @@ SIGNATURES = {
     "tnb_reserve": (_int, [_vp, C.c_size_t]),
     "tnb_workspace_bytes": (C.c_size_t, [_vp]),
     "tnb_launch_count": (C.c_uint64, [_vp]),
+    "tnb_plan_describe": (_int, [_int, _int, _pi64, _pi32, _int, _pi64, _pi32, _int, _pi64, _pi32, _int, _int,
+                                 C.POINTER(PlanDesc), C.c_char_p, C.c_size_t]),
     "tnb_plan_cache_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tnb_plan_cache_clear": (_int, [_vp]),
     "tnb_set_autotune": (_int, [_vp, _int]),
@@ -122,6 +137,38 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+FAMILIES = {0: "ldgsts", 1: "smallk", 2: "tma"}
+
+
+def plan_describe(dims_a, modes_a, dims_b, modes_b, modes_c, dtype=F64, flags=0, num_sms=148):
+    """Dry run of tnb_contract's planner (no GPU, no handle): a dict with the matricised extents M/N/K, the merged
+    mode groups with their strides in A, B and C, and the kernel family / tile the launch would use.  modes_* are
+    hashable labels (ints or strings); the extents of C follow from the operands."""
+    lib = load()
+    labels = {}
+    lab = lambda m: labels.setdefault(m, len(labels))
+    ma = [lab(m) for m in modes_a]; mb = [lab(m) for m in modes_b]
+    ext = dict(zip(modes_a, dims_a)); ext.update(zip(modes_b, dims_b))
+    mc = [lab(m) for m in modes_c]
+    dims_c = [ext.get(m, 0) for m in modes_c]
+    arr = lambda T, v: (T * max(len(v), 1))(*v)
+    d = PlanDesc()
+    err = C.create_string_buffer(512)
+    rc = lib.tnb_plan_describe(dtype, len(ma), arr(C.c_int64, list(dims_a)), arr(C.c_int32, ma),
+                               len(mb), arr(C.c_int64, list(dims_b)), arr(C.c_int32, mb),
+                               len(mc), arr(C.c_int64, dims_c), arr(C.c_int32, mc), flags, num_sms, C.byref(d), err, 512)
+    if rc != 0:
+        raise (DimensionMismatch if rc == 2 else TnbError)(rc, err.value.decode())
+    g = lambda name, n: [int(x) for x in getattr(d, name)[:n]]
+    return {"M": int(d.M), "N": int(d.N), "K": int(d.K), "family": FAMILIES[d.family],
+            "m": {"ext": g("ext_m", d.n_m), "a": g("a_stride_m", d.n_m), "c": g("c_stride_m", d.n_m)},
+            "n": {"ext": g("ext_n", d.n_n), "b": g("b_stride_n", d.n_n), "c": g("c_stride_n", d.n_n)},
+            "k": {"ext": g("ext_k", d.n_k), "a": g("a_stride_k", d.n_k), "b": g("b_stride_k", d.n_k)},
+            "a_k_major": bool(d.a_k_major), "b_k_major": bool(d.b_k_major), "a_vec": int(d.a_vec), "b_vec": int(d.b_vec),
+            "tile": (int(d.tile_m), int(d.tile_n), int(d.tile_k)), "herm_upper": bool(d.herm_upper),
+            "tiles": int(d.tiles), "waves": float(d.waves)}
 
 
 class Handle:

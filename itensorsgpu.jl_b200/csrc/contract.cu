@@ -31,6 +31,7 @@ int launch_smallk_f64(Handle* h, GemmParams& p, cudaStream_t st);
 int launch_smallk_c128(Handle* h, GemmParams& p, cudaStream_t st);
 // TMA-staged kernel for operand pairs that are both K-major (contract_tma.cu)
 bool tma_eligible(const GemmParams& p, int dtype, bool small);
+bool tma_shape_ok(const GemmParams& p, int dtype, bool small);
 int launch_tma(Handle* h, int dtype, GemmParams& p, bool small, cudaStream_t st);
 bool tma_would_split(Handle* h, const GemmParams& p, int dtype, bool small);
 uint64_t tma_split_launches();
@@ -253,55 +254,12 @@ static void set_scalars(GemmParams& p, int dtype, const void* alpha, const void*
   if (beta) { p.beta_re = ((const double*)beta)[0]; if (dtype == TNB_C128) p.beta_im = ((const double*)beta)[1]; }
 }
 
-int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
-                  const void* A, int nB, const int64_t* extB, const int32_t* modeB,
-                  const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
-                  const void* alpha, const void* beta, int flags, cudaStream_t st) {
-  return contract_impl_ex(h, dtype, nA, extA, modeA, A, nB, extB, modeB, B, nC, extC, modeC, C, alpha, beta, flags, st,
-                          nullptr, nullptr, 0);
-}
-
-// strideA / strideB / strideC (optional): element stride of every mode (the operand is then a strided window
-// of a larger tensor);
-// peerC/npeer (optional): the epilogue stores every output element to ALL npeer base pointers (peer-mapped
-// buffers of the other GPUs included) instead of C -- the all-gather of a sharded result fused into the GEMM.
-int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
-                     const void* A, int nB, const int64_t* extB, const int32_t* modeB,
-                     const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
-                     const void* alpha, const void* beta, int flags, cudaStream_t st,
-                     const int64_t* strideC, void* const* peerC, int npeer, const int64_t* strideA,
-                     const int64_t* strideB) {
-  if (npeer < 0 || npeer > TNB_MAX_PEERS) return set_err(h, TNB_ERR_BAD_ARG, "contract: npeer %d", npeer);
-  if (npeer > 0 && beta) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: beta with peer stores");
-  if (dtype != TNB_F64 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: dtype %d", dtype);
-  if (nA < 0 || nB < 0 || nC < 0 || nA > 64 || nB > 64 || nC > 64)
-    return set_err(h, TNB_ERR_BAD_ARG, "contract: bad rank");
-  if (!A || !B || !C) return set_err(h, TNB_ERR_BAD_ARG, "contract: null tensor pointer");
-  // ---- plan cache lookup
-  std::string key;
-  key.reserve(64 + 20 * (nA + nB + nC));
-  auto put = [&](long long x) { key.append((const char*)&x, sizeof(x)); };
-  put(dtype); put(flags & (TNB_CONJ_A | TNB_CONJ_B | TNB_HERM_UPPER)); put(nA); put(nB); put(nC); put(npeer);
-  put(((uintptr_t)A % 16 == 0) | (((uintptr_t)B % 16 == 0) << 1));
-  for (int i = 0; i < nA; ++i) { put(modeA[i]); put(extA[i]); put(strideA ? strideA[i] : -1); }
-  for (int i = 0; i < nB; ++i) { put(modeB[i]); put(extB[i]); put(strideB ? strideB[i] : -1); }
-  for (int i = 0; i < nC; ++i) { put(modeC[i]); put(extC[i]); put(strideC ? strideC[i] : -1); }
-  PlanCache* cache;
-  {
-    std::lock_guard<std::mutex> g(cache_mutex());
-    cache = &caches()[h];
-  }
-  {
-    auto it = cache->map.find(key);
-    if (it != cache->map.end()) {
-      cache->hits++;
-      GemmParams p = it->second.p;
-      p.A = A; p.B = B; p.C = C;
-      set_scalars(p, dtype, alpha, beta);
-      for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
-      return launch_variant(h, dtype, p, it->second.v, st);
-    }
-  }
+// Mode labels -> grouped GEMM description (everything of GemmParams except the operand pointers, the scalars and the
+// peer list).  Pure host logic: no CUDA call, `h` only receives the error text (tnb_plan_describe runs it without a GPU).
+static int plan_from_modes(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA, int nB,
+                           const int64_t* extB, const int32_t* modeB, int nC, const int64_t* extC, const int32_t* modeC,
+                           int flags, const int64_t* strideA, const int64_t* strideB, const int64_t* strideC,
+                           GemmParams& p) {
   std::vector<ModeRec> recs;
   auto find = [&](int label) -> ModeRec* {
     for (auto& r : recs) if (r.label == label) return &r;
@@ -358,7 +316,6 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
   if (k_by_b) std::sort(gk.begin(), gk.end(), [](const ModeRec& x, const ModeRec& y) { return x.posB < y.posB; });
   else std::sort(gk.begin(), gk.end(), [](const ModeRec& x, const ModeRec& y) { return x.posA < y.posA; });
 
-  GemmParams p;
   memset(&p, 0, sizeof(p));
   finish_group(p.gm, gm, 0);
   finish_group(p.gn, gn, 1);
@@ -368,8 +325,6 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
   long long M, N, K;
   if (!total(p.gm, M) || !total(p.gn, N) || !total(p.gk, K)) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: grouped extent exceeds 2^31-1");
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.A = A; p.B = B; p.C = C;
-  set_scalars(p, dtype, alpha, beta);
   p.conjA = (flags & TNB_CONJ_A) ? 1 : 0;
   p.conjB = (flags & TNB_CONJ_B) ? 1 : 0;
   if (flags & TNB_HERM_UPPER) {
@@ -384,6 +339,62 @@ int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const in
     };
     if (c_ascending(p.gm, 1) && c_ascending(p.gn, (long long)p.M)) p.lowerOnly = 2;
   }
+  return TNB_OK;
+}
+
+int contract_impl(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
+                  const void* A, int nB, const int64_t* extB, const int32_t* modeB,
+                  const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                  const void* alpha, const void* beta, int flags, cudaStream_t st) {
+  return contract_impl_ex(h, dtype, nA, extA, modeA, A, nB, extB, modeB, B, nC, extC, modeC, C, alpha, beta, flags, st,
+                          nullptr, nullptr, 0);
+}
+
+// strideA / strideB / strideC (optional): element stride of every mode (the operand is then a strided window
+// of a larger tensor);
+// peerC/npeer (optional): the epilogue stores every output element to ALL npeer base pointers (peer-mapped
+// buffers of the other GPUs included) instead of C -- the all-gather of a sharded result fused into the GEMM.
+int contract_impl_ex(Handle* h, int dtype, int nA, const int64_t* extA, const int32_t* modeA,
+                     const void* A, int nB, const int64_t* extB, const int32_t* modeB,
+                     const void* B, int nC, const int64_t* extC, const int32_t* modeC, void* C,
+                     const void* alpha, const void* beta, int flags, cudaStream_t st,
+                     const int64_t* strideC, void* const* peerC, int npeer, const int64_t* strideA,
+                     const int64_t* strideB) {
+  if (npeer < 0 || npeer > TNB_MAX_PEERS) return set_err(h, TNB_ERR_BAD_ARG, "contract: npeer %d", npeer);
+  if (npeer > 0 && beta) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: beta with peer stores");
+  if (dtype != TNB_F64 && dtype != TNB_C128) return set_err(h, TNB_ERR_UNSUPPORTED, "contract: dtype %d", dtype);
+  if (nA < 0 || nB < 0 || nC < 0 || nA > 64 || nB > 64 || nC > 64)
+    return set_err(h, TNB_ERR_BAD_ARG, "contract: bad rank");
+  if (!A || !B || !C) return set_err(h, TNB_ERR_BAD_ARG, "contract: null tensor pointer");
+  // ---- plan cache lookup
+  std::string key;
+  key.reserve(64 + 20 * (nA + nB + nC));
+  auto put = [&](long long x) { key.append((const char*)&x, sizeof(x)); };
+  put(dtype); put(flags & (TNB_CONJ_A | TNB_CONJ_B | TNB_HERM_UPPER)); put(nA); put(nB); put(nC); put(npeer);
+  put(((uintptr_t)A % 16 == 0) | (((uintptr_t)B % 16 == 0) << 1));
+  for (int i = 0; i < nA; ++i) { put(modeA[i]); put(extA[i]); put(strideA ? strideA[i] : -1); }
+  for (int i = 0; i < nB; ++i) { put(modeB[i]); put(extB[i]); put(strideB ? strideB[i] : -1); }
+  for (int i = 0; i < nC; ++i) { put(modeC[i]); put(extC[i]); put(strideC ? strideC[i] : -1); }
+  PlanCache* cache;
+  {
+    std::lock_guard<std::mutex> g(cache_mutex());
+    cache = &caches()[h];
+  }
+  {
+    auto it = cache->map.find(key);
+    if (it != cache->map.end()) {
+      cache->hits++;
+      GemmParams p = it->second.p;
+      p.A = A; p.B = B; p.C = C;
+      set_scalars(p, dtype, alpha, beta);
+      for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
+      return launch_variant(h, dtype, p, it->second.v, st);
+    }
+  }
+  GemmParams p;
+  TNB_TRY(plan_from_modes(h, dtype, nA, extA, modeA, nB, extB, modeB, nC, extC, modeC, flags, strideA, strideB, strideC, p));
+  p.A = A; p.B = B; p.C = C;
+  set_scalars(p, dtype, alpha, beta);
   p.npeer = npeer;
   for (int g = 0; g < npeer; ++g) p.peerC[g] = peerC[g];
   cache->misses++;
@@ -450,3 +461,50 @@ int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64
 }
 
 }  // namespace tnb
+
+// ---- planner dry run (host only)
+using namespace tnb;
+extern "C" int tnb_plan_describe(int dtype, int nA, const int64_t* extA, const int32_t* modeA, int nB, const int64_t* extB,
+                                 const int32_t* modeB, int nC, const int64_t* extC, const int32_t* modeC, int flags,
+                                 int num_sms, tnb_plan_desc* out, char* err, size_t errlen) {
+  Handle tmp;                      // never touches CUDA: carries num_sms in and the error text out
+  tmp.num_sms = num_sms > 0 ? num_sms : 148;
+  auto fail = [&](int rc) {
+    if (err && errlen) snprintf(err, errlen, "%s", tmp.err.c_str());
+    return rc;
+  };
+  if (!out) return fail(set_err(&tmp, TNB_ERR_BAD_ARG, "plan_describe: null output"));
+  if (dtype != TNB_F64 && dtype != TNB_C128) return fail(set_err(&tmp, TNB_ERR_UNSUPPORTED, "contract: dtype %d", dtype));
+  if (nA < 0 || nB < 0 || nC < 0 || nA > 64 || nB > 64 || nC > 64) return fail(set_err(&tmp, TNB_ERR_BAD_ARG, "contract: bad rank"));
+  if ((nA && (!extA || !modeA)) || (nB && (!extB || !modeB)) || (nC && (!extC || !modeC)))
+    return fail(set_err(&tmp, TNB_ERR_BAD_ARG, "plan_describe: null extent / mode array"));
+  GemmParams p;
+  const int rc = plan_from_modes(&tmp, dtype, nA, extA, modeA, nB, extB, modeB, nC, extC, modeC, flags, nullptr, nullptr, nullptr, p);
+  if (rc) return fail(rc);
+  p.alpha_re = 1.0;                // base pointers stay null: "16-byte aligned operands"
+  const Variant v = choose_variant(&tmp, dtype, p);
+  memset(out, 0, sizeof(*out));
+  out->M = p.M; out->N = p.N; out->K = p.K;
+  out->n_m = p.gm.n; out->n_n = p.gn.n; out->n_k = p.gk.n;
+  for (int i = 0; i < p.gm.n; ++i) { out->ext_m[i] = p.gm.ext[i]; out->a_stride_m[i] = p.gm.sX[i]; out->c_stride_m[i] = p.gm.sY[i]; }
+  for (int i = 0; i < p.gn.n; ++i) { out->ext_n[i] = p.gn.ext[i]; out->b_stride_n[i] = p.gn.sX[i]; out->c_stride_n[i] = p.gn.sY[i]; }
+  for (int i = 0; i < p.gk.n; ++i) { out->ext_k[i] = p.gk.ext[i]; out->a_stride_k[i] = p.gk.sX[i]; out->b_stride_k[i] = p.gk.sY[i]; }
+  const bool cplx = dtype == TNB_C128;
+  const bool a_k1 = p.gk.sX[0] == 1 && p.K > 1, b_k1 = p.gk.sY[0] == 1 && p.K > 1;
+  const bool tma_shape = !v.smallk && a_k1 && b_k1 && tma_shape_ok(p, dtype, v.small);
+  out->family = v.smallk ? 1 : (tma_shape ? 2 : 0);
+  out->a_k_major = v.ak; out->b_k_major = v.bk;
+  out->a_vec = v.va; out->b_vec = v.vb;
+  out->herm_upper = p.lowerOnly == 2;
+  if (v.smallk) {
+    out->tile_m = 256; out->tile_n = p.N; out->tile_k = p.K;
+    out->tiles = ((long long)p.M + 255) / 256;
+  } else {
+    out->tile_m = 64;
+    out->tile_n = cplx ? (v.small ? 32 : 64) : (v.small ? 64 : 128);
+    out->tile_k = cplx ? 8 : 16;           // both tile families: one 128-byte row of K per tile row
+    out->tiles = (((long long)p.M + out->tile_m - 1) / out->tile_m) * (((long long)p.N + out->tile_n - 1) / out->tile_n);
+  }
+  out->waves = (double)out->tiles / (2.0 * tmp.num_sms);
+  return TNB_OK;
+}

@@ -455,9 +455,16 @@ static bool map_ok(const Group& gk, const Group& gf, bool kIsY, int rows, int bk
   return true;
 }
 
+bool tma_shape_ok(const GemmParams& p, int dtype, bool small);
+
 bool tma_eligible(const GemmParams& p, int dtype, bool small) {
   static const bool off = getenv("TNB_TMA") && !strcmp(getenv("TNB_TMA"), "off");
   if (off || !encode_fn()) return false;
+  return tma_shape_ok(p, dtype, small);
+}
+
+// the shape half of the eligibility test (pure host logic; tnb_plan_describe reports it without a driver)
+bool tma_shape_ok(const GemmParams& p, int dtype, bool small) {
   const bool cplx = dtype == TNB_C128;
   const size_t es = cplx ? 16 : 8;
   const int bk = cplx ? 8 : 16;

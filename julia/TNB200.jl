@@ -54,6 +54,29 @@ function NDTensors._contract!(CT::CuDenseTensor{El,NC}, AT::CuDenseTensor{El,NA}
   return data(store(CT))                          # the reference returns parent(Cdata): cudense.jl:330
 end
 
+# ---- planner dry run (no GPU): how a contraction would be matricised -- useful from the REPL when a layout is slow
+struct PlanDesc
+  M::Int64; N::Int64; K::Int64
+  n_m::Int32; n_n::Int32; n_k::Int32; family::Int32
+  ext_m::NTuple{12,Int64}; a_stride_m::NTuple{12,Int64}; c_stride_m::NTuple{12,Int64}
+  ext_n::NTuple{12,Int64}; b_stride_n::NTuple{12,Int64}; c_stride_n::NTuple{12,Int64}
+  ext_k::NTuple{12,Int64}; a_stride_k::NTuple{12,Int64}; b_stride_k::NTuple{12,Int64}
+  a_k_major::Int32; b_k_major::Int32; a_vec::Int32; b_vec::Int32
+  tile_m::Int32; tile_n::Int32; tile_k::Int32; herm_upper::Int32
+  tiles::Int64; waves::Float64
+end
+function plan_describe(::Type{El}, ea::Vector{Int64}, ma::Vector{Int32}, eb::Vector{Int64}, mb::Vector{Int32},
+                       ec::Vector{Int64}, mc::Vector{Int32}; flags::Integer=0, num_sms::Integer=148) where {El}
+  out = Ref{PlanDesc}()
+  err = zeros(UInt8, 512)
+  rc = ccall((:tnb_plan_describe, LIB), Cint,
+             (Cint, Cint, Ptr{Int64}, Ptr{Int32}, Cint, Ptr{Int64}, Ptr{Int32}, Cint, Ptr{Int64}, Ptr{Int32}, Cint, Cint,
+              Ref{PlanDesc}, Ptr{UInt8}, Csize_t),
+             dtype(El), length(ea), ea, ma, length(eb), eb, mb, length(ec), ec, mc, flags, num_sms, out, err, 512)
+  rc == 0 || (rc == 2 ? throw(DimensionMismatch(unsafe_string(pointer(err)))) : throw(ArgumentError(unsafe_string(pointer(err)))))
+  return out[]
+end
+
 # ---- permute!  (src/tensor/cudense.jl:447-478)  and  + / -  (src/tensor/cudense.jl:333-445)
 function permute_axpby!(B::CuDenseTensor{El}, A::CuDenseTensor{El}, α, β) where {El}
   n = length(inds(A))
