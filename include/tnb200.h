@@ -99,6 +99,25 @@ int tnb_kernel_family_counts(tnb_handle_t h, uint64_t* out4);
  * Process-wide setting. */
 int tnb_set_workspace_limit(tnb_handle_t h, size_t bytes);
 size_t tnb_get_workspace_limit(tnb_handle_t h);
+/* Workspace queries -- the `*_bufferSize` calls of this library (the reference gets these implicitly from cuSOLVER /
+ * cuTENSOR, e.g. inside CUSOLVER.svd!/syevd! at src/tensor/culinearalgebra.jl:42,85-87 and the cuTENSOR workspace of
+ * src/tensor/cudense.jl:328).  Pure host arithmetic: no handle, no GPU.  They return the arena bytes the entry point
+ * will require, so a caller can tnb_reserve() once up front (growing the arena later synchronises the device) and plan
+ * HBM for C5-sized bonds; 0 = bad argument.  They honour tnb_set_workspace_limit (whose handle may be NULL).
+ *   tnb_bond_workspace_bytes: op = TNB_WS_HEFF_APPLY (tnb_heff_apply, tnb_noise_term), TNB_WS_FACTORIZE_BOND
+ *     (tnb_factorize_bond, tnb_tebd_apply_gate), TNB_WS_DMRG_BOND_STEP (tnb_dmrg_bond_step: ortho, with_noise and
+ *     krylovdim matter only here); *n_slabs (optional) = number of output-bond slabs H_eff is cut into under the limit.
+ *   tnb_matrix_workspace_bytes: op = TNB_WS_SVD (tnb_svd_trunc), TNB_WS_EIGH (tnb_eigh_trunc, m = n), TNB_WS_QR (tnb_qr). */
+#define TNB_WS_HEFF_APPLY      0
+#define TNB_WS_FACTORIZE_BOND  1
+#define TNB_WS_DMRG_BOND_STEP  2
+#define TNB_WS_SVD             3
+#define TNB_WS_EIGH            4
+#define TNB_WS_QR              5
+struct tnb_bond_dims_s;
+size_t tnb_bond_workspace_bytes(int op, int dtype, const struct tnb_bond_dims_s* dims, int ortho, int with_noise,
+                                int krylovdim, int32_t* n_slabs);
+size_t tnb_matrix_workspace_bytes(int op, int dtype, int64_t m, int64_t n);
 /* Number of kernels this library has launched through the handle (bench `gpu_launches`). */
 uint64_t tnb_launch_count(tnb_handle_t h);
 
@@ -217,7 +236,7 @@ int tnb_qr(tnb_handle_t h, int dtype, int64_t m, int64_t n, const void* A, void*
  * [EXT] ITensors issues through the override surface; anchors are the reference call
  * sites examples/dmrg.jl:25, test/dmrg.jl:27,75. */
 
-typedef struct {
+typedef struct tnb_bond_dims_s {
   int64_t chiL, chiR;   /* MPS bond dims left/right of the two sites */
   int32_t d1, d2;       /* site dims */
   int32_t wL, wM, wR;   /* MPO bond dims: left of site b, between, right of site b+1 */

@@ -68,6 +68,8 @@ SIGNATURES = {
     "tnb_kernel_family_counts": (_int, [_vp, C.POINTER(C.c_uint64)]),
     "tnb_set_workspace_limit": (_int, [_vp, C.c_size_t]),
     "tnb_get_workspace_limit": (C.c_size_t, [_vp]),
+    "tnb_bond_workspace_bytes": (C.c_size_t, [_int, _int, _pbd, _int, _int, _int, _pi32]),
+    "tnb_matrix_workspace_bytes": (C.c_size_t, [_int, _int, _i64, _i64]),
     "tnb_contract": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp, _int, _pi64, _pi32, _vp,
                             _vp, _vp, _int, _vp]),
     "tnb_permute_axpby": (_int, [_vp, _int, _int, _pi64, _pi32, _vp, _pi32, _vp, _vp, _vp, _vp]),
@@ -140,6 +142,33 @@ def load():
 
 
 FAMILIES = {0: "ldgsts", 1: "smallk", 2: "tma"}
+WS_HEFF_APPLY, WS_FACTORIZE_BOND, WS_DMRG_BOND_STEP, WS_SVD, WS_EIGH, WS_QR = range(6)
+
+
+def bond_workspace_bytes(op, chiL, chiR, d1, d2, wL, wM, wR, dtype=F64, ortho=ORTHO_LEFT, noise=False, krylovdim=3):
+    """(arena bytes, H_eff slabs) an entry point needs for one bond -- host arithmetic, no GPU (tnb_bond_workspace_bytes)"""
+    bd = BondDims(chiL, chiR, d1, d2, wL, wM, wR)
+    ns = C.c_int32(0)
+    b = load().tnb_bond_workspace_bytes(op, dtype, C.byref(bd), ortho, 1 if noise else 0, krylovdim, C.byref(ns))
+    if b == 0:
+        raise TnbError(1, "bond_workspace_bytes: bad argument")
+    return int(b), int(ns.value)
+
+
+def matrix_workspace_bytes(op, m, n, dtype=F64):
+    b = load().tnb_matrix_workspace_bytes(op, dtype, m, n)
+    if b == 0:
+        raise TnbError(1, "matrix_workspace_bytes: bad argument")
+    return int(b)
+
+
+def set_workspace_limit(nbytes):
+    """process-wide bound on the pair of H_eff temporaries (0 = default 40 GB); needs no handle"""
+    load().tnb_set_workspace_limit(None, int(nbytes))
+
+
+def get_workspace_limit():
+    return int(load().tnb_get_workspace_limit(None))
 
 
 def plan_describe(dims_a, modes_a, dims_b, modes_b, modes_c, dtype=F64, flags=0, num_sms=148):

@@ -96,6 +96,12 @@ int tnb_create(tnb_handle_t* out) {
       cudaMalloc((void**)&hd->counter, 64) != cudaSuccess ||
       cudaMalloc(&hd->what, 64 * 1024) != cudaSuccess ||
       cudaStreamCreateWithFlags(&hd->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    if (hd->scal) cudaFree(hd->scal);
+    if (hd->scal_host) cudaFreeHost(hd->scal_host);
+    if (hd->partials) cudaFree(hd->partials);
+    if (hd->counter) cudaFree(hd->counter);
+    if (hd->what) cudaFree(hd->what);
     delete hd;
     return TNB_ERR_ALLOC;
   }

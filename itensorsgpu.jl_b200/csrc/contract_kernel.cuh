@@ -558,11 +558,7 @@ template <bool CPLX, bool AK, bool BKM, int VA, int VB, class CFG>
 static int launch_one(Handle* h, GemmParams& p, cudaStream_t st) {
   auto kern = contract_kernel<CPLX, AK, BKM, VA, VB, CFG>;
   constexpr int SM = smem_bytes<CPLX, CFG>();
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-    attr_done = true;
-  }
+  TNB_ONCE_PER_DEVICE(h, TNB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)));
   p.tilesM = (p.M + CFG::BM - 1) / CFG::BM;
   p.tilesN = (p.N + CFG::BN - 1) / CFG::BN;
   p.groupM = 16;

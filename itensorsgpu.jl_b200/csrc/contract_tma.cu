@@ -536,11 +536,7 @@ template <bool CPLX, class CFG>
 static int launch_tma_cfg(Handle* h, GemmParams& p, cudaStream_t st) {
   static const int pd = getenv("TNB_TMA_PD") ? atoi(getenv("TNB_TMA_PD")) : 2;
   auto kern = pd == 3 ? contract_tma_kernel<CPLX, CFG, 3> : contract_tma_kernel<CPLX, CFG, 2>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));
-    attr_done = true;
-  }
+  TNB_ONCE_PER_DEVICE(h, TNB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM)));
   constexpr int BK = CPLX ? 8 : 16;
   p.tilesM = (p.M + CFG::BM - 1) / CFG::BM;
   p.tilesN = (p.N + CFG::BN - 1) / CFG::BN;

@@ -13,6 +13,7 @@
 namespace tnb {
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+int heff_chunks_pub(int dtype, const tnb_bond_dims* d);      // heff.cu: slabs of the output bond under the workspace limit
 
 __global__ void square_kernel(const double* __restrict__ s, double* p, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = s[i] * s[i];
@@ -263,6 +264,26 @@ int factorize_core_pub(Handle* h, int dtype, int64_t m, int64_t n, void* M, int 
 }
 size_t factorize_ws_bytes_pub(int dtype, int64_t m, int64_t n) { return factorize_ws_bytes(dtype, m, n); }
 
+// arena bytes of one tnb_dmrg_bond_step: phi (+ the noise perturbation) pinned at the front, then the larger of the
+// Lanczos stage (H_eff temporaries + krylovdim + 1 vectors) and the factorize stage
+size_t bond_step_ws_bytes(int dtype, const tnb_bond_dims* d, int ortho, bool with_noise, int krylovdim) {
+  const size_t es = elsize(dtype);
+  const int64_t m = d->chiL * d->d1, n = (int64_t)d->d2 * d->chiR;
+  const size_t phib = al256((size_t)m * n * es);
+  const int64_t r = (ortho == TNB_ORTHO_LEFT) ? m : n;
+  const size_t lan = heff_workspace_bytes(dtype, d) + (size_t)(krylovdim + 1) * phib + (1 << 16);
+  size_t need = phib + (with_noise ? al256((size_t)r * r * es) : 0);
+  size_t stage = lan;
+  // factorize workspace (recomputed with the same formula as tnb_factorize_bond)
+  {
+    const int64_t mx = std::max(m, n);
+    size_t t = std::max({svd_ws_bytes(dtype, m, n), eigh_ws_bytes(dtype, mx), qr_ws_bytes(dtype, m, n), qr_ws_bytes(dtype, n, m)});
+    t += 3 * al256((size_t)mx * mx * es) + 4 * al256((size_t)mx * sizeof(double)) + (1 << 16);
+    stage = std::max(stage, t);
+  }
+  return need + stage + (1 << 16);
+}
+
 }  // namespace tnb
 
 using namespace tnb;
@@ -324,23 +345,12 @@ int tnb_dmrg_bond_step(tnb_handle_t h, int dtype, const tnb_bond_dims* d, int64_
   const size_t es = elsize(dtype);
   const int64_t cl = d->chiL, cr = d->chiR, d1 = d->d1, d2 = d->d2;
   const int64_t m = cl * d1, n = d2 * cr;
-  const size_t phib = al256((size_t)m * n * es);
   const int64_t r = (ortho == TNB_ORTHO_LEFT) ? m : n;
   // phi and (optionally) the noise perturbation live in caller-independent device scratch that must
   // survive the Lanczos and factorize arena resets -> allocate them at the very start of the arena
   // and make every later stage allocate after them (no ws_reset in between).
-  const size_t lan = heff_workspace_bytes(dtype, d) + (size_t)(krylovdim + 1) * phib + (1 << 16);
-  size_t need = phib + (noise > 0 ? al256((size_t)r * r * es) : 0);
-  size_t stage = lan;
-  // factorize workspace (recomputed with the same formula as tnb_factorize_bond)
-  {
-    const int64_t mx = std::max(m, n);
-    size_t t = std::max({svd_ws_bytes(dtype, m, n), eigh_ws_bytes(dtype, mx), qr_ws_bytes(dtype, m, n), qr_ws_bytes(dtype, n, m)});
-    t += 3 * al256((size_t)mx * mx * es) + 4 * al256((size_t)mx * sizeof(double)) + (1 << 16);
-    stage = std::max(stage, t);
-  }
   ws_reset(H);
-  TNB_TRY(ws_require(H, need + stage + (1 << 16)));
+  TNB_TRY(ws_require(H, bond_step_ws_bytes(dtype, d, ortho, noise > 0, krylovdim)));
   void *phi, *rho = nullptr;
   TNB_TRY(ws_alloc(H, (size_t)m * n * es, &phi));
   if (noise > 0) TNB_TRY(ws_alloc(H, (size_t)r * r * es, &rho));
@@ -530,5 +540,31 @@ int tnb_tebd_gate_bform(tnb_handle_t h, int dtype, int64_t chiL, int64_t chiM, i
   if (truncerr) *truncerr = err;
   return check_cuda(H, cudaStreamSynchronize(ST), "tebd_gate_bform sync");
 }
+
+// ---- workspace queries (the *_bufferSize calls of this library): host arithmetic only, no handle, no GPU
+size_t tnb_bond_workspace_bytes(int op, int dtype, const tnb_bond_dims* d, int ortho, int with_noise, int krylovdim,
+                                int32_t* n_slabs) {
+  if (!d || (dtype != TNB_F64 && dtype != TNB_C128)) return 0;
+  if (d->chiL < 1 || d->chiR < 1 || d->d1 < 1 || d->d2 < 1 || d->wL < 1 || d->wM < 1 || d->wR < 1) return 0;
+  if (n_slabs) *n_slabs = heff_chunks_pub(dtype, d);
+  const int64_t m = d->chiL * d->d1, n = (int64_t)d->d2 * d->chiR;
+  switch (op) {
+    case TNB_WS_HEFF_APPLY: return heff_workspace_bytes(dtype, d);
+    case TNB_WS_FACTORIZE_BOND: return factorize_ws_bytes(dtype, m, n);
+    case TNB_WS_DMRG_BOND_STEP: return bond_step_ws_bytes(dtype, d, ortho, with_noise != 0, krylovdim < 1 ? 3 : krylovdim);
+    default: return 0;
+  }
+}
+
+size_t tnb_matrix_workspace_bytes(int op, int dtype, int64_t m, int64_t n) {
+  if ((dtype != TNB_F64 && dtype != TNB_C128) || m < 1 || n < 1) return 0;
+  switch (op) {
+    case TNB_WS_SVD: return svd_ws_bytes(dtype, m, n) + 2 * al256(std::min(m, n) * 8) + 4096;
+    case TNB_WS_EIGH: return m == n ? eigh_ws_bytes(dtype, n) + al256(n * 8) + 4096 : 0;
+    case TNB_WS_QR: return qr_ws_bytes(dtype, m, n);
+    default: return 0;
+  }
+}
+
 
 }  // extern "C"

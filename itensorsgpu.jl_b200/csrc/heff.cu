@@ -789,6 +789,7 @@ int heff_core_pub(Handle* h, int dtype, const tnb_bond_dims* d, const void* L, c
   return heff_apply_any(h, dtype, d, L, W1, W2, R, phi, out, t0, t1, st);
 }
 
+int heff_chunks_pub(int dtype, const tnb_bond_dims* d) { return heff_nchunks(dtype, d); }
 void set_ws_limit(size_t bytes) { g_ws_limit = bytes ? bytes : ((size_t)40 << 30); }
 size_t get_ws_limit() { return g_ws_limit; }
 
@@ -801,7 +802,7 @@ using namespace tnb;
 extern "C" {
 
 int tnb_set_workspace_limit(tnb_handle_t h, size_t bytes) {
-  if (!h) return TNB_ERR_BAD_ARG;
+  (void)h;                        // process-wide setting: a null handle is accepted (host-only planning queries)
   set_ws_limit(bytes);
   return TNB_OK;
 }

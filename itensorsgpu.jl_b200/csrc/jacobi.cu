@@ -411,8 +411,7 @@ static int jacobi_run(Handle* h, int64_t m, int64_t n, const void* A, int64_t ld
 
   auto eig = small_eigh_kernel<CPLX, NB2>;
   constexpr int SMEM = 2 * NB2 * (NB2 + 1) * (int)sizeof(T);
-  static bool attr = false;
-  if (!attr) { TNB_CUDA(h, cudaFuncSetAttribute(eig, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); attr = true; }
+  TNB_ONCE_PER_DEVICE(h, TNB_CUDA(h, cudaFuncSetAttribute(eig, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)));
 
   const double tol = std::max(1e-14, std::sqrt((double)m) * 2.3e-16);
   const int steps = (k == 1) ? 1 : (int)nblk - 1;

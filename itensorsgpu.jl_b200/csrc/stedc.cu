@@ -615,14 +615,12 @@ int stedc_impl(Handle* h, int64_t n, double* d, double* e, double** Qres, double
     h->launches++;
   }
   constexpr int LEAF_SMEM = 2 * DC_LEAF * (DC_LEAF + 1) * (int)sizeof(double);
-  static bool leaf_attr = false;
-  if (!leaf_attr) { TNB_CUDA(h, cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM)); leaf_attr = true; }
+  TNB_ONCE_PER_DEVICE(h, TNB_CUDA(h, cudaFuncSetAttribute(dc_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM)));
   dc_leaf_kernel<<<L, 256, LEAF_SMEM, st>>>(d, e, d_bounds, (double*)Qa, n, B.dcur, B.idx);
   h->launches++;
   TNB_CUDA(h, cudaStreamSynchronize(st));     // host descriptor vectors are about to be reused / go out of scope
 
-  static bool attr = false;
-  if (!attr) { TNB_CUDA(h, cudaFuncSetAttribute(dc_m1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024)); attr = true; }
+  TNB_ONCE_PER_DEVICE(h, TNB_CUDA(h, cudaFuncSetAttribute(dc_m1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024)));
   double *Qin = (double*)Qa, *Qout = (double*)Qb;
   std::vector<int> hk(nmax);
   for (int l = 1; l <= levels; ++l) {

@@ -192,6 +192,19 @@ int eigh_impl(Handle* h, int dtype, int64_t n, void* A, int64_t kmax, int64_t ks
               cudaStream_t st);
 int qr_impl(Handle* h, int dtype, int64_t m, int64_t n, const void* A, void* Q, void* R, cudaStream_t st);
 
+// cudaFuncSetAttribute applies to the CURRENT device only: remember per device what has been set, so that a process
+// owning one handle per GPU (julia: CUDA.device!; python: tn.handle() after torch.cuda.set_device) works on all of them.
+constexpr int TNB_MAX_DEVICES = 64;
+#define TNB_ONCE_PER_DEVICE(h, stmt)                          \
+  do {                                                        \
+    static bool _done[tnb::TNB_MAX_DEVICES] = {};             \
+    const int _dv = (h)->device & (tnb::TNB_MAX_DEVICES - 1); \
+    if (!_done[_dv]) {                                        \
+      stmt;                                                   \
+      _done[_dv] = true;                                      \
+    }                                                         \
+  } while (0)
+
 inline size_t elsize(int dtype) { return dtype == TNB_C128 ? 16 : 8; }
 
 }  // namespace tnb

@@ -592,12 +592,8 @@ static int tridiag_core(Handle* h, int64_t n, void* Av, double* d, double* e, vo
   T* P = (T*)Pv;
   int nbt_prev = 0;            // > 0: the previous column's y lives in P slots (K2S), else in ybuf (K2)
   bool lower_valid_only = false;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNB_CUDA(h, cudaFuncSetAttribute(td_k2_kernel<CPLX, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    TNB_CUDA(h, cudaFuncSetAttribute(td_k2_kernel<CPLX, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done = true;
-  }
+  TNB_ONCE_PER_DEVICE(h, TNB_CUDA(h, cudaFuncSetAttribute(td_k2_kernel<CPLX, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                      TNB_CUDA(h, cudaFuncSetAttribute(td_k2_kernel<CPLX, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)));
   TNB_CUDA(h, cudaMemsetAsync(tau, 0, (size_t)n * sizeof(T), st));
   const double one[2] = {1.0, 0.0}, mone[2] = {-1.0, 0.0};
   auto k1 = [&](int64_t i, int jp, int do_column) {

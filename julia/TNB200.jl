@@ -54,6 +54,14 @@ function NDTensors._contract!(CT::CuDenseTensor{El,NC}, AT::CuDenseTensor{El,NA}
   return data(store(CT))                          # the reference returns parent(Cdata): cudense.jl:330
 end
 
+# ---- workspace queries (host arithmetic; no GPU): reserve the arena once instead of growing it mid-sweep
+bond_workspace_bytes(op::Integer, ::Type{El}, d::BondDims; ortho::Integer=0, noise::Bool=false, krylovdim::Integer=3) where {El} =
+  ccall((:tnb_bond_workspace_bytes, LIB), Csize_t, (Cint, Cint, Ref{BondDims}, Cint, Cint, Cint, Ptr{Int32}),
+        op, dtype(El), d, ortho, noise ? 1 : 0, krylovdim, C_NULL)
+matrix_workspace_bytes(op::Integer, ::Type{El}, m::Integer, n::Integer) where {El} =
+  ccall((:tnb_matrix_workspace_bytes, LIB), Csize_t, (Cint, Cint, Int64, Int64), op, dtype(El), m, n)
+reserve!(nbytes::Integer) = check(ccall((:tnb_reserve, LIB), Cint, (Ptr{Cvoid}, Csize_t), handle(), nbytes))
+
 # ---- planner dry run (no GPU): how a contraction would be matricised -- useful from the REPL when a layout is slow
 struct PlanDesc
   M::Int64; N::Int64; K::Int64
