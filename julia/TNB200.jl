@@ -400,4 +400,113 @@ function dmrg_sweep!(A::Vector{<:CuArray{ElT}}, W::Vector{<:CuArray{ElT}}, env::
   return e[], merr[], be, bt
 end
 
+# =====================================================================================================
+# Remaining entry points of include/tnb200.h, so that every exported symbol has a Julia binding
+# (tests/test_julia_glue.py checks names, argument counts and argument classes against the header).
+# =====================================================================================================
+# ---- scalar * and /  (src/tensor/cudense.jl:22,502): in place, no allocation
+function scale!(x::CuArray{El}, α::Number) where {El}
+  a = Ref(El(α))
+  check(ccall((:tnb_scale, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(El), length(x), ptr(x), a, stream()))
+  return x
+end
+# ---- dot = scalar(dag(A)*B)  (src/tensor/cudense.jl:25-26): device reduction + one 16-byte readback
+function dot(x::CuArray{El}, y::CuArray{El}) where {El}
+  r = Ref{ComplexF64}(0)
+  check(ccall((:tnb_dot, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(El), length(x), ptr(x), ptr(y), C_NULL, r, stream()))
+  return El <: Real ? real(r[]) : r[]
+end
+
+# ---- handle housekeeping / introspection
+function destroy!()
+  HANDLE[] == C_NULL && return
+  check(ccall((:tnb_destroy, LIB), Cint, (Ptr{Cvoid},), HANDLE[])); HANDLE[] = C_NULL
+end
+version() = ccall((:tnb_version, LIB), Cint, ())
+workspace_bytes() = ccall((:tnb_workspace_bytes, LIB), Csize_t, (Ptr{Cvoid},), handle())
+launch_count() = ccall((:tnb_launch_count, LIB), UInt64, (Ptr{Cvoid},), handle())
+workspace_limit() = ccall((:tnb_get_workspace_limit, LIB), Csize_t, (Ptr{Cvoid},), C_NULL)
+function plan_cache_stats()               # the `ContractionPlans` analogue (src/ITensorsGPU.jl:54-55)
+  v = [Ref{UInt64}(0) for _ in 1:4]
+  check(ccall((:tnb_plan_cache_stats, LIB), Cint, (Ptr{Cvoid}, Ref{UInt64}, Ref{UInt64}, Ref{UInt64}, Ref{UInt64}),
+              handle(), v[1], v[2], v[3], v[4]))
+  return (entries=v[1][], hits=v[2][], misses=v[3][], autotuned=v[4][])
+end
+plan_cache_clear!() = check(ccall((:tnb_plan_cache_clear, LIB), Cint, (Ptr{Cvoid},), handle()))
+function kernel_family_counts()
+  v = zeros(UInt64, 4)
+  check(ccall((:tnb_kernel_family_counts, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}), handle(), v))
+  return (ldgsts=v[1], smallk=v[2], tma=v[3], tma_split_k=v[4])
+end
+
+# ---- host-buffer H_eff*phi: pinned host phi in, H*phi out, the PCIe copies pipelined behind steps 1 and 4
+function heff_apply_host!(out_host::Vector{ElT}, L::CuArray{ElT,3}, W1::CuArray{ElT,4}, W2::CuArray{ElT,4}, R::CuArray{ElT,3},
+                          phi_host::Vector{ElT}, d::BondDims) where {ElT}
+  check(ccall((:tnb_heff_apply_host, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), Ref(d), ptr(L), ptr(W1), ptr(W2), ptr(R), pointer(phi_host), pointer(out_host), stream()))
+  return out_host
+end
+
+# ---- multi-GPU (one process per GPU): slab form without the fused gather, peer group, sharded DMRG pieces
+function heff_apply_shard!(out_slab::CuArray{ElT,4}, Lslab::CuArray{ElT,3}, W1::CuArray{ElT,4}, W2::CuArray{ElT,4},
+                           R::CuArray{ElT,3}, phi::CuArray{ElT,4}) where {ElT}
+  check(ccall((:tnb_heff_apply_shard, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), bond_dims(phi, W1, W2), size(Lslab, 2), ptr(Lslab), ptr(W1), ptr(W2), ptr(R), ptr(phi),
+              ptr(out_slab), stream()))
+  return out_slab
+end
+peer_close(p::Ptr{Cvoid}) = check(ccall((:tnb_peer_close, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle(), p))
+peer_free(p::Ptr{Cvoid}) = check(ccall((:tnb_peer_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle(), p))
+peer_status() = check(ccall((:tnb_peer_status, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle(), stream()))
+comm_finalize() = check(ccall((:tnb_comm_finalize, LIB), Cint, (Ptr{Cvoid},), handle()))
+comm_barrier() = check(ccall((:tnb_comm_barrier, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), handle(), stream()))
+"every rank's region [off + rank*nbytes, +nbytes) of bufs[rank] lands in the same region of every peer buffer"
+comm_allgather(bufs::Vector{Ptr{Cvoid}}, off::Integer, nbytes::Integer) =
+  check(ccall((:tnb_comm_allgather, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Csize_t, Csize_t, Ptr{Cvoid}),
+              handle(), bufs, off, nbytes, stream()))
+shard_stage_bytes(::Type{El}, chi::Integer, d::Integer, w::Integer, world::Integer) where {El} =
+  ccall((:tnb_shard_stage_bytes, LIB), Csize_t, (Cint, Int64, Int32, Int32, Cint), dtype(El), chi, d, w, world)
+# environments stored as l' slabs per rank (never moved); stage_peers = peer-mapped staging buffers of every rank
+function env_update_left_shard!(Lnew_slab::CuArray{ElT}, Lslab::CuArray{ElT}, A::CuArray{ElT,3}, W::CuArray{ElT,4},
+                                stage_peers::Vector{Ptr{Cvoid}}) where {ElT}
+  chiL, d, chiR = size(A)
+  check(ccall((:tnb_env_update_left_shard, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), chiL, chiR, d, size(W, 1), size(W, 4), ptr(Lslab), ptr(A), ptr(W), stage_peers, ptr(Lnew_slab), stream()))
+  return Lnew_slab
+end
+function env_update_right_shard!(Rnew::CuArray{ElT}, R::CuArray{ElT}, A::CuArray{ElT,3}, W::CuArray{ElT,4},
+                                 stage_peers::Vector{Ptr{Cvoid}}) where {ElT}
+  chiL, d, chiR = size(A)
+  check(ccall((:tnb_env_update_right_shard, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), chiL, chiR, d, size(W, 1), size(W, 4), ptr(R), ptr(A), ptr(W), stage_peers, ptr(Rnew), stream()))
+  return Rnew
+end
+# Lanczos with the matvec sharded over l'; out_a / out_b: the two alternating peer-mapped full-vector buffers
+function eigsolve_lanczos_shard!(phi::CuArray{ElT,4}, Lslab, W1, W2, R, out_a::Vector{Ptr{Cvoid}}, out_b::Vector{Ptr{Cvoid}};
+                                 krylovdim::Int=3, maxiter::Int=1, tol::Float64=1e-14) where {ElT}
+  e, nmv = Ref{Float64}(0), Ref{Cint}(0)
+  check(ccall((:tnb_eigsolve_lanczos_shard, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}},
+               Cint, Cint, Float64, Ref{Float64}, Ref{Cint}, Ptr{Cvoid}),
+              handle(), dtype(ElT), bond_dims(phi, W1, W2), ptr(Lslab), ptr(W1), ptr(W2), ptr(R), ptr(phi), out_a, out_b,
+              krylovdim, maxiter, tol, e, nmv, stream()))
+  return e[], Int(nmv[])
+end
+# host-buffer form of the sharded matvec: this rank uploads 1/world of phi and downloads its own l' slab of H*phi
+function heff_apply_shard_host!(out_host::Vector{ElT}, Lslab, W1, W2, R, phi_host::Vector{ElT}, d::BondDims,
+                                phi_peers::Vector{Ptr{Cvoid}}, out_peers::Vector{Ptr{Cvoid}}) where {ElT}
+  check(ccall((:tnb_heff_apply_shard_host, LIB), Cint,
+              (Ptr{Cvoid}, Cint, Ref{BondDims}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}},
+               Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(), dtype(ElT), Ref(d), ptr(Lslab), ptr(W1), ptr(W2), ptr(R), pointer(phi_host), phi_peers, out_peers,
+              pointer(out_host), stream()))
+  return out_host
+end
+
 end # module
