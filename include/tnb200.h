@@ -152,6 +152,14 @@ int tnb_plan_describe(int dtype,
                       int nB, const int64_t* extB, const int32_t* modeB,
                       int nC, const int64_t* extC, const int32_t* modeC,
                       int flags, int num_sms, tnb_plan_desc* out, char* err, size_t errlen);
+/* Same with explicit element strides per mode (NULL = dense column-major): the operand is then a strided WINDOW of a
+ * larger tensor, which is how the fixed-workspace and multi-GPU entry points address slabs of L, R, A and of the output
+ * vector without copying them (tnb_set_workspace_limit, tnb_heff_apply_shard_fused, tnb_env_update_*_shard). */
+int tnb_plan_describe_strided(int dtype,
+                              int nA, const int64_t* extA, const int32_t* modeA, const int64_t* strideA,
+                              int nB, const int64_t* extB, const int32_t* modeB, const int64_t* strideB,
+                              int nC, const int64_t* extC, const int32_t* modeC, const int64_t* strideC,
+                              int flags, int num_sms, tnb_plan_desc* out, char* err, size_t errlen);
 
 /* ------------------------------------------------------------------ tier 1: primitives - */
 

@@ -62,6 +62,8 @@ SIGNATURES = {
     "tnb_launch_count": (C.c_uint64, [_vp]),
     "tnb_plan_describe": (_int, [_int, _int, _pi64, _pi32, _int, _pi64, _pi32, _int, _pi64, _pi32, _int, _int,
                                  C.POINTER(PlanDesc), C.c_char_p, C.c_size_t]),
+    "tnb_plan_describe_strided": (_int, [_int, _int, _pi64, _pi32, _pi64, _int, _pi64, _pi32, _pi64, _int, _pi64, _pi32, _pi64,
+                                         _int, _int, C.POINTER(PlanDesc), C.c_char_p, C.c_size_t]),
     "tnb_plan_cache_stats": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tnb_plan_cache_clear": (_int, [_vp]),
     "tnb_set_autotune": (_int, [_vp, _int]),
@@ -171,10 +173,12 @@ def get_workspace_limit():
     return int(load().tnb_get_workspace_limit(None))
 
 
-def plan_describe(dims_a, modes_a, dims_b, modes_b, modes_c, dtype=F64, flags=0, num_sms=148):
+def plan_describe(dims_a, modes_a, dims_b, modes_b, modes_c, dtype=F64, flags=0, num_sms=148, strides_a=None,
+                  strides_b=None, strides_c=None):
     """Dry run of tnb_contract's planner (no GPU, no handle): a dict with the matricised extents M/N/K, the merged
     mode groups with their strides in A, B and C, and the kernel family / tile the launch would use.  modes_* are
-    hashable labels (ints or strings); the extents of C follow from the operands."""
+    hashable labels (ints or strings); the extents of C follow from the operands.  strides_* (optional, elements per
+    mode) describe operands that are strided windows of larger tensors."""
     lib = load()
     labels = {}
     lab = lambda m: labels.setdefault(m, len(labels))
@@ -185,9 +189,11 @@ def plan_describe(dims_a, modes_a, dims_b, modes_b, modes_c, dtype=F64, flags=0,
     arr = lambda T, v: (T * max(len(v), 1))(*v)
     d = PlanDesc()
     err = C.create_string_buffer(512)
-    rc = lib.tnb_plan_describe(dtype, len(ma), arr(C.c_int64, list(dims_a)), arr(C.c_int32, ma),
-                               len(mb), arr(C.c_int64, list(dims_b)), arr(C.c_int32, mb),
-                               len(mc), arr(C.c_int64, dims_c), arr(C.c_int32, mc), flags, num_sms, C.byref(d), err, 512)
+    st = lambda v: arr(C.c_int64, list(v)) if v is not None else None
+    rc = lib.tnb_plan_describe_strided(dtype, len(ma), arr(C.c_int64, list(dims_a)), arr(C.c_int32, ma), st(strides_a),
+                                       len(mb), arr(C.c_int64, list(dims_b)), arr(C.c_int32, mb), st(strides_b),
+                                       len(mc), arr(C.c_int64, dims_c), arr(C.c_int32, mc), st(strides_c), flags, num_sms,
+                                       C.byref(d), err, 512)
     if rc != 0:
         raise (DimensionMismatch if rc == 2 else TnbError)(rc, err.value.decode())
     g = lambda name, n: [int(x) for x in getattr(d, name)[:n]]

@@ -464,9 +464,24 @@ int gemm_batched_impl(Handle* h, int dtype, char opA, char opB, int64_t m, int64
 
 // ---- planner dry run (host only)
 using namespace tnb;
+extern "C" int tnb_plan_describe_strided(int dtype, int nA, const int64_t* extA, const int32_t* modeA, const int64_t* strideA,
+                                         int nB, const int64_t* extB, const int32_t* modeB, const int64_t* strideB, int nC,
+                                         const int64_t* extC, const int32_t* modeC, const int64_t* strideC, int flags,
+                                         int num_sms, tnb_plan_desc* out, char* err, size_t errlen);
+
 extern "C" int tnb_plan_describe(int dtype, int nA, const int64_t* extA, const int32_t* modeA, int nB, const int64_t* extB,
                                  const int32_t* modeB, int nC, const int64_t* extC, const int32_t* modeC, int flags,
                                  int num_sms, tnb_plan_desc* out, char* err, size_t errlen) {
+  return tnb_plan_describe_strided(dtype, nA, extA, modeA, nullptr, nB, extB, modeB, nullptr, nC, extC, modeC, nullptr, flags,
+                                   num_sms, out, err, errlen);
+}
+
+// strideX (optional, elements): the operand is a strided window of a larger tensor -- how the chunked / sharded DMRG
+// entry points address slabs of L, R, A and the output vector (heff.cu, shardops.cu)
+extern "C" int tnb_plan_describe_strided(int dtype, int nA, const int64_t* extA, const int32_t* modeA, const int64_t* strideA,
+                                         int nB, const int64_t* extB, const int32_t* modeB, const int64_t* strideB, int nC,
+                                         const int64_t* extC, const int32_t* modeC, const int64_t* strideC, int flags,
+                                         int num_sms, tnb_plan_desc* out, char* err, size_t errlen) {
   Handle tmp;                      // never touches CUDA: carries num_sms in and the error text out
   tmp.num_sms = num_sms > 0 ? num_sms : 148;
   auto fail = [&](int rc) {
@@ -479,7 +494,7 @@ extern "C" int tnb_plan_describe(int dtype, int nA, const int64_t* extA, const i
   if ((nA && (!extA || !modeA)) || (nB && (!extB || !modeB)) || (nC && (!extC || !modeC)))
     return fail(set_err(&tmp, TNB_ERR_BAD_ARG, "plan_describe: null extent / mode array"));
   GemmParams p;
-  const int rc = plan_from_modes(&tmp, dtype, nA, extA, modeA, nB, extB, modeB, nC, extC, modeC, flags, nullptr, nullptr, nullptr, p);
+  const int rc = plan_from_modes(&tmp, dtype, nA, extA, modeA, nB, extB, modeB, nC, extC, modeC, flags, strideA, strideB, strideC, p);
   if (rc) return fail(rc);
   p.alpha_re = 1.0;                // base pointers stay null: "16-byte aligned operands"
   const Variant v = choose_variant(&tmp, dtype, p);

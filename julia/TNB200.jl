@@ -85,6 +85,20 @@ function plan_describe(::Type{El}, ea::Vector{Int64}, ma::Vector{Int32}, eb::Vec
   return out[]
 end
 
+"plan_describe for operands that are strided windows of larger tensors (element strides per mode)"
+function plan_describe_strided(::Type{El}, ea::Vector{Int64}, ma::Vector{Int32}, sa::Vector{Int64}, eb::Vector{Int64},
+                               mb::Vector{Int32}, sb::Vector{Int64}, ec::Vector{Int64}, mc::Vector{Int32}, sc::Vector{Int64};
+                               flags::Integer=0, num_sms::Integer=148) where {El}
+  out = Ref{PlanDesc}()
+  err = zeros(UInt8, 512)
+  rc = ccall((:tnb_plan_describe_strided, LIB), Cint,
+             (Cint, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Int32},
+              Ptr{Int64}, Cint, Cint, Ref{PlanDesc}, Ptr{UInt8}, Csize_t),
+             dtype(El), length(ea), ea, ma, sa, length(eb), eb, mb, sb, length(ec), ec, mc, sc, flags, num_sms, out, err, 512)
+  rc == 0 || (rc == 2 ? throw(DimensionMismatch(unsafe_string(pointer(err)))) : throw(ArgumentError(unsafe_string(pointer(err)))))
+  return out[]
+end
+
 # ---- permute!  (src/tensor/cudense.jl:447-478)  and  + / -  (src/tensor/cudense.jl:333-445)
 function permute_axpby!(B::CuDenseTensor{El}, A::CuDenseTensor{El}, α, β) where {El}
   n = length(inds(A))

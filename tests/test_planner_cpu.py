@@ -198,3 +198,97 @@ def test_random_contractions_property():
         la = list(rng.permutation(labs_k + labs_m)); lb = list(rng.permutation(labs_k + labs_n))
         lc = list(rng.permutation(labs_m + labs_n))
         _check(tn, dims, la, lb, lc, cplx=bool(trial & 1), seed=trial)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Strided windows: the fixed-workspace (tnb_set_workspace_limit) and multi-GPU entry points never copy a slab of L, R, A
+# or of the output vector -- they hand the planner a base pointer inside the stored tensor plus per-mode strides
+# (csrc/heff.cu: heff_core / heff_apply_any / env_update_impl / heff_shard_fused_host_tail).  The cases below replay
+# exactly those call sites (same extents, mode labels, strides and base offsets) on the CPU.
+# ---------------------------------------------------------------------------------------------------------------------
+def _replay_window(plan, a_flat, b_flat, c_flat, conj_b=False):
+    """like _replay, but C is a window of a larger buffer: writes land in place, everything else stays untouched"""
+    om_a, om_c = _offsets(plan["m"]["ext"], plan["m"]["a"]), _offsets(plan["m"]["ext"], plan["m"]["c"])
+    on_b, on_c = _offsets(plan["n"]["ext"], plan["n"]["b"]), _offsets(plan["n"]["ext"], plan["n"]["c"])
+    ok_a, ok_b = _offsets(plan["k"]["ext"], plan["k"]["a"]), _offsets(plan["k"]["ext"], plan["k"]["b"])
+    Bm = b_flat[ok_b[:, None] + on_b[None, :]]
+    dest = (om_c[:, None] + on_c[None, :]).reshape(-1)
+    assert len(np.unique(dest)) == dest.size and dest.min() >= 0 and dest.max() < c_flat.size
+    c_flat[dest] = (a_flat[om_a[:, None] + ok_a[None, :]] @ (np.conj(Bm) if conj_b else Bm)).reshape(-1)
+    return dest
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_heff_slab_of_the_output_bond_as_strided_windows(cplx):
+    """heff_apply_any: slab j of l' -- step 1 reads L[:, l'_j, :] as a window of the stored L, step 4 writes
+    out[l'_j, :, :, :] as a window of the full output vector.  Steps 2+3 are dense and done by the oracle here."""
+    tn = _tn()
+    from oracle import dmrg as od
+    rng = np.random.default_rng(5)
+    cl, cr, d, w, G = 12, 10, 2, 3, 3
+    clp = cl // G
+    mk = (lambda s: rng.standard_normal(s) + 1j * rng.standard_normal(s)) if cplx else rng.standard_normal
+    L, R, W1, W2, phi = mk((cl, cl, w)), mk((cr, cr, w)), mk((w, d, d, w)), mk((w, d, d, w)), mk((cl, d, d, cr))
+    want = od.heff_apply(L, W1, W2, R, phi)
+    out = np.full(cl * d * d * cr, np.nan, dtype=want.dtype)
+    dt = tn._lib.C128 if cplx else tn._lib.F64
+    for j in range(G):
+        # step 1: T1[s1,s2,r,l'_c,a] = phi[l,s1,s2,r] L[l,l'_c,a], L window: strides {1, cl, cl*lp_stored}, base j*clp*cl
+        p1 = tn._lib.plan_describe((cl, d, d, cr), ("l", "s1", "s2", "r"), (cl, clp, w), ("l", "lp", "a"),
+                                   ("s1", "s2", "r", "lp", "a"), dtype=dt, strides_b=(1, cl, cl * cl))
+        t1 = _replay(p1, ot.flat(phi), ot.flat(L)[j * clp * cl:], d * d * cr * clp * w)
+        T1 = ot.unflat(t1, (d, d, cr, clp, w))
+        ref1, _ = ot.contract(phi, ("l", "s1", "s2", "r"), L[:, j * clp:(j + 1) * clp, :], ("l", "lp", "a"))
+        assert ot.rel_err(T1, ref1) < 1e-13
+        # steps 2, 3 (dense): -> T3[r, l'_c, s1', s2', c]
+        T2, _ = ot.contract(T1, ("s1", "s2", "r", "lp", "a"), W1, ("a", "s1", "s1p", "b"))       # (s2,r,lp,s1p,b)
+        T3, l3 = ot.contract(T2, ("s2", "r", "lp", "s1p", "b"), W2, ("b", "s2", "s2p", "c"))     # (r,lp,s1p,s2p,c)
+        assert l3 == ("r", "lp", "s1p", "s2p", "c")
+        # step 4: out[l'_c,s1',s2',r'] = T3 R[r,r',c], C window: strides {1, cl, cl*d, cl*d*d}, base j*clp
+        p4 = tn._lib.plan_describe((cr, clp, d, d, w), ("r", "lp", "s1p", "s2p", "c"), (cr, cr, w), ("r", "rp", "c"),
+                                   ("lp", "s1p", "s2p", "rp"), dtype=dt, strides_c=(1, cl, cl * d, cl * d * d))
+        assert p4["m"]["c"][0] == 1 and p4["n"]["c"] == [cl * d * d]
+        _replay_window(p4, ot.flat(T3), ot.flat(R), out[j * clp:])
+    assert not np.any(np.isnan(out))                         # the G windows tile the output vector exactly
+    assert ot.rel_err(ot.unflat(out, (cl, d, d, cr)), want) < 1e-12
+
+
+def test_environment_update_chunks_and_host_tail_windows():
+    """env_update_impl (left): chunk j of the bra bond l' -- E window {1, cl, cl*cl} at j*cc*cl in the first contraction,
+    conj(A) window {1, cl, cl*d} at j*cc in the last one, accumulated over chunks; heff_shard_fused_host_tail: R window
+    over r' and an output window strided in both l' (rank slab) and r' (chunk)."""
+    tn = _tn()
+    from oracle import dmrg as od
+    rng = np.random.default_rng(6)
+    cl, cr, d, wl, wr, G = 8, 6, 2, 3, 2, 2
+    cc = cl // G
+    E, A, W = rng.standard_normal((cl, cl, wl)), rng.standard_normal((cl, d, cr)), rng.standard_normal((wl, d, d, wr))
+    want = od.env_left_update(E, A, W)
+    acc = np.zeros(cr * cr * wr)
+    for j in range(G):
+        p1 = tn._lib.plan_describe((cl, cc, wl), ("l", "lp", "a"), (cl, d, cr), ("l", "s", "r"), ("lp", "a", "s", "r"),
+                                   strides_a=(1, cl, cl * cl))
+        T1 = ot.unflat(_replay(p1, ot.flat(E)[j * cc * cl:], ot.flat(A), cc * wl * d * cr), (cc, wl, d, cr))
+        T2, _ = ot.contract(T1, ("lp", "a", "s", "r"), W, ("a", "s", "sp", "b"))
+        T2 = ot.permute(T2, ("lp", "r", "sp", "b"), ("lp", "r", "sp", "b"))
+        p3 = tn._lib.plan_describe((cc, cr, d, wr), ("lp", "r", "sp", "b"), (cc, d, cr), ("lp", "sp", "rp"), ("r", "rp", "b"),
+                                   strides_b=(1, cl, cl * d), flags=tn._lib.CONJ_B)
+        part = np.zeros(cr * cr * wr)
+        _replay_window(p3, ot.flat(T2), ot.flat(A)[j * cc:], part, conj_b=True)
+        acc += part                                           # beta = 1 accumulation over the chunks
+    assert ot.rel_err(ot.unflat(acc, (cr, cr, wr)), want) < 1e-12
+
+    # host tail: rank `rank` of `world` owns l' slab [rank*clp, +clp); step 4 is cut over r' into pieces [q0, q1)
+    cl, cr, d, w, world, rank = 8, 9, 2, 3, 2, 1
+    clp = cl // world
+    T3, R = rng.standard_normal((cr, clp, d, d, w)), rng.standard_normal((cr, cr, w))
+    ref, _ = ot.contract(T3, ("r", "lp", "s1p", "s2p", "c"), R, ("r", "rp", "c"))
+    full = np.full(cl * d * d * cr, np.nan)
+    col = cl * d * d
+    for q0, q1 in ((0, 3), (3, 6), (6, 9)):
+        p = tn._lib.plan_describe((cr, clp, d, d, w), ("r", "lp", "s1p", "s2p", "c"), (cr, q1 - q0, w), ("r", "rp", "c"),
+                                  ("lp", "s1p", "s2p", "rp"), strides_b=(1, cr, cr * cr), strides_c=(1, cl, cl * d, cl * d * d))
+        _replay_window(p, ot.flat(T3), ot.flat(R)[q0 * cr:], full[rank * clp + q0 * col:])
+    got = ot.unflat(full, (cl, d, d, cr))
+    assert ot.rel_err(got[rank * clp:(rank + 1) * clp], ref) < 1e-13
+    assert np.all(np.isnan(got[:rank * clp]))                 # the other rank's slab is not touched
