@@ -111,3 +111,17 @@ def test_matrix_queries_and_bad_arguments(lib):
         lib.bond_workspace_bytes(lib.WS_HEFF_APPLY, 0, 4, 2, 2, 5, 5, 5)
     with pytest.raises(lib.TnbError):
         lib.bond_workspace_bytes(lib.WS_HEFF_APPLY, 4, 4, 2, 2, 5, 5, 5, dtype=9)
+
+
+def test_shard_staging_buffer_matches_the_c5_multi_gpu_run(lib):
+    """tnb_shard_stage_bytes: the peer-mapped staging buffer of the sharded environment updates / noise term.  At C5
+    on 8 GPUs it is the full-size noise-term temporary, 64.4 GB per GPU -- the '64 GB of it the noise-term staging
+    buffer' of BASELINE.md section 4 (profiles/r02_c5_chi8192_n8.json: 142 GB of HBM in use per GPU)."""
+    L = lib.load()
+    b = L.tnb_shard_stage_bytes(lib.F64, 8192, 2, 30, 8)
+    assert b == 8192 * 8192 * 2 * 2 * 30 * 8 + 4096
+    assert 64.0 < b / GB < 64.5
+    # C3: the noise term dominates the two environment regions as well
+    b3 = L.tnb_shard_stage_bytes(lib.F64, 4096, 2, 5, 8)
+    assert b3 == 4096 * 4096 * 4 * 5 * 8 + 4096
+    assert L.tnb_shard_stage_bytes(lib.C128, 4096, 2, 5, 2) == 2 * (b3 - 4096) + 4096
