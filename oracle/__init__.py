@@ -35,7 +35,8 @@ for this path (see ``tests/test_oracle_pins.py``):
 * ``test/test_cuiterativesolvers.jl:22,26``  davidson eigen-residual.
 * ``test/test_cumps.jl:208-226``  orthogonality to 1e-12.
 * BASELINE.json configs[0] (ITensors.jl's stock ``examples/dmrg.jl`` schedule, N=100 S=1 chain): the converged
-  energy that example publishes, -138.940086 -- the one absolute number from outside this repository that exercises
+  energy that example publishes, -138.940086 (quoted from memory of the ITensors.jl README / SURVEY.md 8c: there
+  is no network here to re-fetch it) -- the one absolute number from outside this repository that exercises
   the whole [EXT] restatement at once (MPO, environments, Lanczos, factorize rule, truncation, sweep order).
 * ``tests/golden/hotpath_small.npz``: the outputs of this package on seeded inputs, one case per entry point, committed
   with their generator; ``tests/test_golden_cpu.py`` fails if a change here moves any of them.

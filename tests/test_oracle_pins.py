@@ -314,7 +314,7 @@ def test_shard_layout_helpers_on_the_host():
 
 # ---- BASELINE.json configs[0] = ITensors.jl's stock examples/dmrg.jl schedule (N=100 S=1 chain, 5 sweeps,
 # maxdim 10/20/100/100/200).  The converged energy that example prints, -138.940086 (six decimals; ITensors.jl README /
-# White & Huse's S=1 chain), is the one absolute number outside this repo that pins the WHOLE [EXT] restatement at once:
+# White & Huse's S=1 chain -- quoted from memory as in SURVEY.md 8c, there is no network to re-fetch it), is the one absolute number outside this repo that pins the WHOLE [EXT] restatement at once:
 # MPO construction, environments, Lanczos (krylovdim 3, maxiter 1), the factorize rule, truncation and the sweep
 # order.  The start state differs (Julia's RNG cannot be reproduced), so only the converged value is comparable.
 def test_dmrg_c1_spin_one_chain_n100_converges_to_the_published_energy():
